@@ -1,0 +1,85 @@
+// host_common.cuh -- host-side plumbing shared by the C-ABI translation units:
+// error reporting, stream-ordered temporaries, host<->device staging.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ecb200.h"
+
+namespace ecb200 {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define ECB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::ecb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ECB200_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define ECB_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    ::ecb200::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      ::ecb200::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ECB200_ERR_CUDA;                                                            \
+    }                                                                                    \
+  } while (0)
+
+inline int layout_of(uint32_t flags) { return (int)(flags & ECB200_LAYOUT_MASK); }
+inline bool on_device(uint32_t flags) { return (flags & ECB200_MEM_MASK) == ECB200_MEM_DEVICE; }
+inline bool quirk_on(uint32_t flags) { return (flags & ECB200_NO_QUIRK) == 0; }
+
+inline int check_common(size_t n, uint32_t flags) {
+  const int L = layout_of(flags);
+  if (L != (int)ECB200_LAYOUT_LANE && L != (int)ECB200_LAYOUT_PACK4 && L != (int)ECB200_LAYOUT_SOA) {
+    set_error("unknown layout %d", L);
+    return ECB200_ERR_ARG;
+  }
+  if (L == (int)ECB200_LAYOUT_PACK4 && (n & 3)) {
+    set_error("PACK4 layout needs n %% 4 == 0 (n = %zu)", n);
+    return ECB200_ERR_ARG;
+  }
+  return ECB200_OK;
+}
+
+// One call's worth of device temporaries (stream-ordered; freed on the same stream).
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+  int alloc(void** out, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(out, bytes, stream);
+    if (e != cudaSuccess) {
+      set_error("cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return e == cudaErrorMemoryAllocation ? ECB200_ERR_NOMEM : ECB200_ERR_CUDA;
+    }
+    ptrs.push_back(*out);
+    return ECB200_OK;
+  }
+};
+
+// An operand of a batched call: pointer + number of 256-bit coordinates per lane.
+struct Operand {
+  const void* in;   // input pointer (caller space) or nullptr
+  void* out;        // output pointer (caller space) or nullptr
+  int nc;
+  void* dev;        // device pointer the kernel uses (filled by stage_*)
+};
+
+inline size_t operand_bytes(size_t n, int nc) { return n * (size_t)nc * 32; }
+
+}  // namespace ecb200

@@ -1,0 +1,297 @@
+// kernels_point.cu -- co-Z point kernels and the batched scalar multiplication, one
+// lane per thread, plus their C-ABI entry points (include/ecb200.h).
+//
+// All point kernels read and write the device-native planar layout (ECB200_LAYOUT_SOA:
+// coalesced 128-bit accesses); other layouts and host memory go through the conversion
+// kernels of kernels_field.cu.  The scalar multiplication is integer-multiply bound
+// (211 540 MAC32 per lane against 224 bytes of traffic), so the conversion passes are
+// noise there.
+#include "host_common.cuh"
+#include "layout.cuh"
+#include "point.cuh"
+
+namespace ecb200 {
+
+int convert_to_soa(int L, void* dst, const void* src, size_t n, int nc, cudaStream_t s);
+int convert_from_soa(int L, void* dst, const void* src, size_t n, int nc, cudaStream_t s);
+
+using S = Layout<L_SOA>;
+
+__device__ __forceinline__ jac load_jac(const void* p, size_t n, size_t i) {
+  jac r;
+  r.x = S::load(p, n, i, 3, 0);
+  r.y = S::load(p, n, i, 3, 1);
+  r.z = S::load(p, n, i, 3, 2);
+  return r;
+}
+__device__ __forceinline__ void store_jac(void* p, size_t n, size_t i, const jac& a) {
+  S::store(p, n, i, 3, 0, a.x);
+  S::store(p, n, i, 3, 1, a.y);
+  S::store(p, n, i, 3, 2, a.z);
+}
+
+enum PointOp : int { PO_DBLU, PO_ZADDU, PO_ZDAU, PO_ADDZ21, PO_TRPLU };
+
+template <int OP, bool QUIRK>
+__global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __restrict__ out2, const void* __restrict__ A,
+                                               const void* __restrict__ B, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jac a = load_jac(A, n, i);
+  if (OP == PO_DBLU) {
+    const jac r = pt_dblu<QUIRK>(a);
+    store_jac(out1, n, i, a);
+    store_jac(out2, n, i, r);
+  } else if (OP == PO_TRPLU) {
+    const jac r = pt_trplu<QUIRK>(a);
+    store_jac(out1, n, i, a);
+    store_jac(out2, n, i, r);
+  } else if (OP == PO_ZADDU) {
+    const jac b = load_jac(B, n, i);
+    const jac r = pt_zaddu<QUIRK>(a, b);
+    store_jac(out1, n, i, a);
+    store_jac(out2, n, i, r);
+  } else if (OP == PO_ZDAU) {
+    jac q = load_jac(B, n, i);
+    const jac r = pt_zdau<QUIRK>(a, q);
+    store_jac(out1, n, i, q);
+    store_jac(out2, n, i, r);
+  } else if (OP == PO_ADDZ21) {
+    const fe bx = S::load(B, n, i, 3, 0), by = S::load(B, n, i, 3, 1);
+    store_jac(out1, n, i, pt_add_z2_1<QUIRK>(a, bx, by));
+  }
+}
+
+// mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per lane
+// unless k_bcast (scalar_mult_1s: one scalar for all lanes).
+template <bool QUIRK, int MODE>
+__global__ void __launch_bounds__(128) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
+                                                     size_t n, int k_bcast) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : S::load(k, n, i, 1, 0);
+  fe px, py;
+  if (MODE == 0) {
+    px = S::load(P, n, i, 3, 0);
+    py = S::load(P, n, i, 3, 1);
+  } else {
+    const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
+    px = fe_const(gx);
+    py = fe_const(gy);
+  }
+  const jac r = pt_scalar_mult<QUIRK>(kk.v, px, py);
+  store_jac(out, n, i, r);
+}
+
+template <bool QUIRK>
+__global__ void __launch_bounds__(128) k_to_affine(void* __restrict__ xy, const void* __restrict__ J, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const jac a = load_jac(J, n, i);
+  // jacobian_curve_point.h:33-42: invZ = z^(p-2); x = X*invZ^2; y = Y*invZ^3; to_classical
+  const uint32_t e[8] = {0xfffffffdu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 1u, 0xffffffffu};
+  fe res = fe_R(), base = a.z;
+#pragma unroll 1
+  for (int b = 0; b < 256; b++) {
+    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base);
+    if (b < 255) base = fp_sqr<QUIRK>(base);
+  }
+  const fe iz2 = fp_sqr<QUIRK>(res);
+  const fe iz3 = fp_mul(iz2, res);
+  S::store(xy, n, i, 2, 0, fp_to_classical(fp_mul(a.x, iz2)));
+  S::store(xy, n, i, 2, 1, fp_to_classical(fp_mul(a.y, iz3)));
+}
+
+__global__ void __launch_bounds__(256) k_from_affine(void* __restrict__ J, const void* __restrict__ xy, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jac r;
+  r.x = fp_from_classical(S::load(xy, n, i, 2, 0));
+  r.y = fp_from_classical(S::load(xy, n, i, 2, 1));
+  r.z = fe_R();
+  store_jac(J, n, i, r);
+}
+
+// ---- host-side staging: bring every operand to a device SOA buffer and back --------------
+struct Staged {
+  Scratch sc;
+  cudaStream_t s;
+  uint32_t flags;
+  size_t n;
+  struct Out { void* user; void* dev_soa; void* dev_raw; int nc; };
+  std::vector<Out> outs;
+  Staged(cudaStream_t st, uint32_t f, size_t nn) : sc(st), s(st), flags(f), n(nn) {}
+
+  // returns a device SOA pointer holding the input
+  int in(const void* user, int nc, const void** dev) {
+    const int L = layout_of(flags);
+    const size_t bytes = operand_bytes(n, nc);
+    const void* raw = user;
+    int rc;
+    if (!on_device(flags)) {
+      void* d;
+      if ((rc = sc.alloc(&d, bytes))) return rc;
+      ECB_CUDA(cudaMemcpyAsync(d, user, bytes, cudaMemcpyHostToDevice, s));
+      raw = d;
+    }
+    if (L == L_SOA) { *dev = raw; return ECB200_OK; }
+    void* soa;
+    if ((rc = sc.alloc(&soa, bytes))) return rc;
+    if ((rc = convert_to_soa(L, soa, raw, n, nc, s))) return rc;
+    *dev = soa;
+    return ECB200_OK;
+  }
+  int out(void* user, int nc, void** dev) {
+    const int L = layout_of(flags);
+    const size_t bytes = operand_bytes(n, nc);
+    int rc;
+    Out o{user, nullptr, nullptr, nc};
+    if (on_device(flags) && L == L_SOA) { o.dev_soa = user; }
+    else {
+      if ((rc = sc.alloc(&o.dev_soa, bytes))) return rc;
+      if (L != L_SOA) {
+        if (on_device(flags)) o.dev_raw = user;
+        else if ((rc = sc.alloc(&o.dev_raw, bytes))) return rc;
+      }
+    }
+    outs.push_back(o);
+    *dev = o.dev_soa;
+    return ECB200_OK;
+  }
+  int finish() {
+    const int L = layout_of(flags);
+    int rc;
+    for (auto& o : outs) {
+      const size_t bytes = operand_bytes(n, o.nc);
+      const void* src = o.dev_soa;
+      if (L != L_SOA) {
+        if ((rc = convert_from_soa(L, o.dev_raw, o.dev_soa, n, o.nc, s))) return rc;
+        src = o.dev_raw;
+      }
+      if (!on_device(flags)) ECB_CUDA(cudaMemcpyAsync(o.user, src, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    if (!on_device(flags)) ECB_CUDA(cudaStreamSynchronize(s));
+    return ECB200_OK;
+  }
+};
+
+template <int OP>
+static int point_call(void* out1, void* out2, const void* A, const void* B, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  const bool two_out = OP != PO_ADDZ21, two_in = (OP == PO_ZADDU || OP == PO_ZDAU || OP == PO_ADDZ21);
+  if (!out1 || !A || (two_out && !out2) || (two_in && !B)) {
+    set_error("null pointer argument");
+    return ECB200_ERR_ARG;
+  }
+  Staged st((cudaStream_t)stream, flags, n);
+  const void *dA = nullptr, *dB = nullptr;
+  void *d1 = nullptr, *d2 = nullptr;
+  if ((rc = st.in(A, 3, &dA))) return rc;
+  if (two_in && (rc = st.in(B, 3, &dB))) return rc;
+  if ((rc = st.out(out1, 3, &d1))) return rc;
+  if (two_out && (rc = st.out(out2, 3, &d2))) return rc;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (quirk_on(flags)) k_point<OP, true><<<blocks, 128, 0, st.s>>>(d1, d2, dA, dB, n);
+  else k_point<OP, false><<<blocks, 128, 0, st.s>>>(d1, d2, dA, dB, n);
+  ECB_LAUNCH_CHECK();
+  return st.finish();
+}
+
+static int scalar_mult_call(void* out, const void* k, const void* P, int mode, int k_bcast, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  if (!out || !k || (mode == 0 && !P)) {
+    set_error("null pointer argument");
+    return ECB200_ERR_ARG;
+  }
+  Staged st((cudaStream_t)stream, flags, n);
+  const void *dk = nullptr, *dP = nullptr;
+  void* dout = nullptr;
+  if (k_bcast) {
+    void* d;
+    if ((rc = st.sc.alloc(&d, 32))) return rc;
+    ECB_CUDA(cudaMemcpyAsync(d, k, 32, cudaMemcpyHostToDevice, st.s));
+    dk = d;
+  } else if ((rc = st.in(k, 1, &dk))) return rc;
+  if (mode == 0 && (rc = st.in(P, 3, &dP))) return rc;
+  if ((rc = st.out(out, 3, &dout))) return rc;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  const bool q = quirk_on(flags);
+  if (mode == 0) {
+    if (q) k_scalar_mult<true, 0><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    else k_scalar_mult<false, 0><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+  } else {
+    if (q) k_scalar_mult<true, 1><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    else k_scalar_mult<false, 1><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+  }
+  ECB_LAUNCH_CHECK();
+  return st.finish();
+}
+
+}  // namespace ecb200
+
+using namespace ecb200;
+
+extern "C" {
+
+int ecb200_dblu(void* outP, void* out2, const void* P, size_t n, uint32_t flags, void* stream) {
+  return point_call<PO_DBLU>(outP, out2, P, nullptr, n, flags, stream);
+}
+int ecb200_zaddu(void* outP, void* outR, const void* P, const void* O, size_t n, uint32_t flags, void* stream) {
+  return point_call<PO_ZADDU>(outP, outR, P, O, n, flags, stream);
+}
+int ecb200_zdau(void* outQ, void* outR, const void* P, const void* Q, size_t n, uint32_t flags, void* stream) {
+  return point_call<PO_ZDAU>(outQ, outR, P, Q, n, flags, stream);
+}
+int ecb200_add_z2_1(void* outR, const void* A, const void* B, size_t n, uint32_t flags, void* stream) {
+  return point_call<PO_ADDZ21>(outR, nullptr, A, B, n, flags, stream);
+}
+int ecb200_trplu(void* outP, void* out3, const void* P, size_t n, uint32_t flags, void* stream) {
+  return point_call<PO_TRPLU>(outP, out3, P, nullptr, n, flags, stream);
+}
+int ecb200_scalar_mult_p256(void* out, const void* k, const void* P, size_t n, uint32_t flags, void* stream) {
+  return scalar_mult_call(out, k, P, 0, 0, n, flags, stream);
+}
+int ecb200_scalar_mult_p256_base(void* out, const void* k, size_t n, uint32_t flags, void* stream) {
+  return scalar_mult_call(out, k, nullptr, 1, 0, n, flags, stream);
+}
+int ecb200_scalar_mult_p256_1s(void* out, const uint32_t* k1, const void* P, size_t n, uint32_t flags, void* stream) {
+  return scalar_mult_call(out, k1, P, 0, 1, n, flags, stream);
+}
+
+int ecb200_from_affine(void* outJ, const void* xy, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  if (!outJ || !xy) { set_error("null pointer argument"); return ECB200_ERR_ARG; }
+  Staged st((cudaStream_t)stream, flags, n);
+  const void* din = nullptr;
+  void* dout = nullptr;
+  if ((rc = st.in(xy, 2, &din))) return rc;
+  if ((rc = st.out(outJ, 3, &dout))) return rc;
+  k_from_affine<<<(unsigned)((n + 255) / 256), 256, 0, st.s>>>(dout, din, n);
+  ECB_LAUNCH_CHECK();
+  return st.finish();
+}
+
+int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  if (!xy || !J) { set_error("null pointer argument"); return ECB200_ERR_ARG; }
+  Staged st((cudaStream_t)stream, flags, n);
+  const void* din = nullptr;
+  void* dout = nullptr;
+  if ((rc = st.in(J, 3, &din))) return rc;
+  if ((rc = st.out(xy, 2, &dout))) return rc;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (quirk_on(flags)) k_to_affine<true><<<blocks, 128, 0, st.s>>>(dout, din, n);
+  else k_to_affine<false><<<blocks, 128, 0, st.s>>>(dout, din, n);
+  ECB_LAUNCH_CHECK();
+  return st.finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+/* ecb200.h -- C ABI of the B200-native batched NIST P-256 engine.
+ *
+ * This is the drop-in boundary for ONE hot path of aguinet/ecsimd: Montgomery
+ * field ops mod p256 -> co-Z Jacobian point ops -> scalar_mult_p256.  Every
+ * entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).  The reference is a header-only C++20 template library
+ * with a single compiled symbol (lib/scalar_mult_p256.cpp:12-14) operating on
+ * one 4-lane AVX2 pack per call; this ABI is the batched form of the same
+ * functions: n independent lanes per call, plain pointers and sizes.
+ *
+ * All functions return ECB200_OK (0) or a negative error code and never throw;
+ * ecb200_last_error() gives the message for the calling thread.  Like the
+ * reference, no input validation is performed on values: out-of-contract
+ * inputs (non-canonical field elements, Z != R, ...) give the same
+ * deterministic garbage as the reference does.
+ *
+ * DATA LAYOUTS (flags & ECB200_LAYOUT_MASK); a "value" is a 256-bit integer:
+ *   ECB200_LAYOUT_LANE   value i = 8 x u32 (= 4 x u64, little-endian host),
+ *                        least-significant word first, at byte offset 32*i.
+ *                        Points: X|Y|Z (96 B) or x|y (64 B) per lane.
+ *   ECB200_LAYOUT_PACK4  the reference's in-memory pack layout
+ *                        (include/ecsimd/bignum.h:101-102, eve::wide<struct>):
+ *                        lanes are grouped by 4; inside a 128-byte pack the
+ *                        u64 word index is limb*4 + lane.  A Jacobian pack
+ *                        (include/ecsimd/jacobian_curve_point.h:64-67) is
+ *                        X-pack | Y-pack | Z-pack = 384 B; an affine pack
+ *                        (curve_point.h:40-42) is x-pack | y-pack = 256 B.
+ *                        n must be a multiple of 4.  An array of
+ *                        wide_bignum<bignum_256> / wide_jacobian_curve_point
+ *                        objects can be passed as is.
+ *   ECB200_LAYOUT_SOA    device-native planar layout: a buffer of n values is
+ *                        two planes of n x uint4 (16 B): plane 0 = words 0..3,
+ *                        plane 1 = words 4..7.  A buffer of n points with C
+ *                        coordinates is 2*C planes (X lo, X hi, Y lo, ...).
+ *                        Every warp-wide access is a fully coalesced 128-bit
+ *                        load/store.
+ * MEMORY SPACE (flags & ECB200_MEM_MASK):
+ *   ECB200_MEM_HOST      pointers are host memory; the call stages the data
+ *                        through device buffers owned by the library and
+ *                        returns when the outputs are written (synchronous).
+ *   ECB200_MEM_DEVICE    pointers are device memory on the current CUDA device;
+ *                        kernels are enqueued on `stream` (a cudaStream_t, may
+ *                        be NULL for the default stream) and the call returns
+ *                        without synchronising.
+ * ECB200_NO_QUIRK        compute mathematically exact squares instead of
+ *                        reproducing the reference's lost-carry squaring defect
+ *                        (include/ecsimd/mul.h:192-206).  Default (flag clear)
+ *                        is bit-exact parity with the reference.
+ */
+#ifndef ECB200_H
+#define ECB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define ECB200_ABI_VERSION 1
+
+#define ECB200_OK 0
+#define ECB200_ERR_ARG (-1)
+#define ECB200_ERR_CUDA (-2)
+#define ECB200_ERR_NOMEM (-3)
+
+#define ECB200_LAYOUT_LANE 0u
+#define ECB200_LAYOUT_PACK4 1u
+#define ECB200_LAYOUT_SOA 2u
+#define ECB200_LAYOUT_MASK 0xfu
+#define ECB200_MEM_HOST 0u
+#define ECB200_MEM_DEVICE 0x10u
+#define ECB200_MEM_MASK 0x10u
+#define ECB200_NO_QUIRK 0x100u
+
+/* ---- library ------------------------------------------------------------- */
+int ecb200_abi_version(void);
+/* Select the CUDA device used by the calling thread for subsequent calls and
+ * check that it is an sm_100 part. */
+int ecb200_init(int device);
+/* Release the staging buffers owned by the library on the current device. */
+int ecb200_shutdown(void);
+const char* ecb200_last_error(void);
+/* Number of kernels launched by this library in this process so far. */
+uint64_t ecb200_launch_count(void);
+
+/* ---- Montgomery field ops (include/ecsimd/mgry_ops.h) ----------------------- */
+/* out = mgry_add(a,b)            mgry_ops.h:10-13 (modular.h:10-15) */
+int ecb200_mgry_add(void* out, const void* a, const void* b, size_t n, uint32_t flags, void* stream);
+/* out = mgry_sub(a,b)            mgry_ops.h:26-29 (modular.h:24-41) */
+int ecb200_mgry_sub(void* out, const void* a, const void* b, size_t n, uint32_t flags, void* stream);
+/* out = mgry_mul(a,b)            mgry_ops.h:31-35 (mul.h:150-158, mgry_mul.h:84-121) */
+int ecb200_mgry_mul(void* out, const void* a, const void* b, size_t n, uint32_t flags, void* stream);
+/* out = mgry_sqr(a)              mgry_ops.h:37-42 (mul.h:160-221) */
+int ecb200_mgry_sqr(void* out, const void* a, size_t n, uint32_t flags, void* stream);
+/* out = mgry_shift_left<count>(a), count in 1..8   mgry_ops.h:15-24 */
+int ecb200_mgry_shift_left(void* out, const void* a, int count, size_t n, uint32_t flags, void* stream);
+/* out = GFp::opposite(a)         gfp.h:60-64 */
+int ecb200_gfp_opposite(void* out, const void* a, size_t n, uint32_t flags, void* stream);
+/* out = wide_mgry_bignum::from_classical(a) / to_classical()   mgry.h:47-55 */
+int ecb200_from_classical(void* out, const void* a, size_t n, uint32_t flags, void* stream);
+int ecb200_to_classical(void* out, const void* a, size_t n, uint32_t flags, void* stream);
+/* out = GFp::inverse(a) = a^(p-2)   gfp.h:42-44 (mgry_ops.h:44-86) */
+int ecb200_gfp_inverse(void* out, const void* a, size_t n, uint32_t flags, void* stream);
+/* Repeated multiply, register resident: out = a * b^iters (iters Montgomery
+ * multiplications per lane with one load and one store) -- the kernel the IMAD
+ * roofline of the multiplier is measured with. */
+int ecb200_mgry_mul_chain(void* out, const void* a, const void* b, int iters, size_t n, uint32_t flags, void* stream);
+
+/* ---- co-Z Jacobian point ops (include/ecsimd/curve_group.h) ---------------- */
+/* Points are Jacobian, Montgomery form, 3 coordinates (X,Y,Z). */
+/* out2 = DBLU(P) (= 2P), outP = P rewritten              curve_group.h:64-87 */
+int ecb200_dblu(void* outP, void* out2, const void* P, size_t n, uint32_t flags, void* stream);
+/* outR = ZADDU(P,O) (= P+O), outP = P rewritten          curve_group.h:91-116 */
+int ecb200_zaddu(void* outP, void* outR, const void* P, const void* O, size_t n, uint32_t flags, void* stream);
+/* outR = ZDAU(P,Q) (= 2P+Q), outQ = Q rewritten          curve_group.h:120-153 */
+int ecb200_zdau(void* outQ, void* outR, const void* P, const void* Q, size_t n, uint32_t flags, void* stream);
+/* outR = ADD_Z2_1(A,B), Z(B) == R                         curve_group.h:155-179 */
+int ecb200_add_z2_1(void* outR, const void* A, const void* B, size_t n, uint32_t flags, void* stream);
+/* out3 = TRPLU(P) (= 3P), outP = P rewritten             curve_group.h:183-186 */
+int ecb200_trplu(void* outP, void* out3, const void* P, size_t n, uint32_t flags, void* stream);
+
+/* ---- scalar multiplication ---------------------------------------------------- */
+/* out[i] = scalar_mult_p256(k[i], P[i])   lib/scalar_mult_p256.cpp:12-14
+ *        = curve_group<curve_nist_p256>::scalar_mult   curve_group.h:189-218
+ * k: n raw 256-bit scalars (not reduced mod the group order);
+ * P: n Jacobian points with Z == R (as produced by from_affine); out: n Jacobian
+ * points, Montgomery form, the same (X:Y:Z) representative as the reference. */
+int ecb200_scalar_mult_p256(void* out, const void* k, const void* P, size_t n, uint32_t flags, void* stream);
+/* Same with P = the generator for every lane (curve_group::WJG(), curve_group.h:39-41). */
+int ecb200_scalar_mult_p256_base(void* out, const void* k, size_t n, uint32_t flags, void* stream);
+/* scalar_mult_1s: one scalar (8 x u32, host memory) for all lanes   curve_group.h:221-251 */
+int ecb200_scalar_mult_p256_1s(void* out, const uint32_t* k1, const void* P, size_t n, uint32_t flags, void* stream);
+
+/* ---- affine <-> Jacobian ------------------------------------------------------- */
+/* outJ = wide_jacobian_curve_point::from_affine(xy)   jacobian_curve_point.h:25-31
+ * xy: classical affine (x,y), 2 coordinates. */
+int ecb200_from_affine(void* outJ, const void* xy, size_t n, uint32_t flags, void* stream);
+/* xy = J.to_affine()                                   jacobian_curve_point.h:33-42 */
+int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* stream);
+
+/* ---- synthetic inputs, generated on the device (bench / large parity runs) ------ */
+/* value i = 4 x splitmix64 words of counter (seed * 0x100000001B3 + 4*(start+i) + limb);
+ * kind 0: raw 256 bits (scalars); kind 1: canonical field element (minus p once if >= p). */
+int ecb200_synth_values(void* out, uint64_t seed, uint64_t start, int kind, size_t n, uint32_t flags, void* stream);
+/* XOR-fold of all 32-bit words of a device buffer into 8 words (order independent
+ * checksum used by the multi-GPU parity tests); out8: host memory, 8 x u32. */
+int ecb200_checksum(uint32_t* out8, const void* buf, size_t nwords, void* stream);
+
+/* ---- integer-pipe micro-benchmarks (roofline denominators) ------------------------ */
+/* which: 0 IMAD.WIDE.U32 (independent chains)  1 IMAD.LO+IMAD.HI pairs  2 IADD3 chains
+ *        3 IMAD.WIDE + IADD3 interleaved 1:1     4 IMAD.WIDE.U32.X carry chains
+ *        5 VIMNMX3                               6 IMAD.WIDE + IADD3 interleaved 1:2
+ * Runs `blocks` x `threads` threads for `iters` loop trips on `stream`, returns the
+ * number of counted instructions per thread per trip in *ops_per_iter and the
+ * elapsed milliseconds (CUDA events) in *ms. */
+int ecb200_microbench(int which, int blocks, int threads, int iters, double* ops_per_iter, float* ms, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECB200_H */

@@ -447,6 +447,18 @@ DEF_RANGE(r_trplu, { jac p, r; memcpy(&p, g->a + 24 * i, 96); TRPLU(&r, &p);
                      memcpy(g->o + 24 * i, &p, 96); memcpy(g->o2 + 24 * i, &r, 96); })
 DEF_RANGE(r_smul, { jac p, r; memcpy(&p, g->b + 24 * i, 96); scalar_mult(&r, g->a + 8 * i, &p);
                     memcpy(g->o + 24 * i, &r, 96); })
+typedef struct { u32* o; const u32 *k, *P; u32* wraps; } wargs_t;
+static void r_smul_wraps(void* c, size_t lo, size_t hi) {
+  wargs_t* g = (wargs_t*)c;
+  for (size_t i = lo; i < hi; i++) {
+    jac p, r;
+    u64 before = g_cnt[5];
+    memcpy(&p, g->P + 24 * i, 96);
+    scalar_mult(&r, g->k + 8 * i, &p);
+    memcpy(g->o + 24 * i, &r, 96);
+    g->wraps[i] = (u32)(g_cnt[5] - before);
+  }
+}
 DEF_RANGE(r_fa, { jac r; from_affine(&r, g->a + 16 * i); memcpy(g->o + 24 * i, &r, 96); })
 DEF_RANGE(r_ta, { jac p; memcpy(&p, g->a + 24 * i, 96); to_affine(g->o + 16 * i, &p); })
 DEF_RANGE(r_fx, g->ok[i] = (uint8_t)from_x(g->o + 8 * i, g->a + 8 * i))
@@ -471,6 +483,11 @@ void orc_zdau(u32* outQ, u32* outR, const u32* P, const u32* Q, size_t n, int nt
 void orc_add_z2_1(u32* outR, const u32* A, const u32* B, size_t n, int nt) { RUN(r_addz, outR, 0, A, B, 0); }
 void orc_trplu(u32* outP, u32* out3, const u32* P, size_t n, int nt) { RUN(r_trplu, outP, out3, P, 0, 0); }
 void orc_scalar_mult(u32* out, const u32* k, const u32* P, size_t n, int nt) { RUN(r_smul, out, 0, k, P, 0); }
+/* scalar_mult that also reports, per lane, how many times square() lost a carry */
+void orc_scalar_mult_wraps(u32* out, u32* wraps, const u32* k, const u32* P, size_t n, int nt) {
+  wargs_t g = {out, k, P, wraps};
+  par_range(n, nt, r_smul_wraps, &g);
+}
 void orc_from_affine(u32* outJ, const u32* xy, size_t n, int nt) { RUN(r_fa, outJ, 0, xy, 0, 0); }
 void orc_to_affine(u32* xy, const u32* J, size_t n, int nt) { RUN(r_ta, xy, 0, J, 0, 0); }
 void orc_from_x(u32* y, uint8_t* ok, const u32* x, size_t n, int nt) { RUN(r_fx, y, 0, x, 0, ok); }

@@ -48,6 +48,7 @@ void orc_zdau(uint32_t* outQ, uint32_t* outR, const uint32_t* P, const uint32_t*
 void orc_add_z2_1(uint32_t* outR, const uint32_t* A, const uint32_t* B, size_t n, int nt);
 void orc_trplu(uint32_t* outP, uint32_t* out3, const uint32_t* P, size_t n, int nt);
 void orc_scalar_mult(uint32_t* out, const uint32_t* k, const uint32_t* P, size_t n, int nt);
+void orc_scalar_mult_wraps(uint32_t* out, uint32_t* wraps, const uint32_t* k, const uint32_t* P, size_t n, int nt);
 void orc_from_affine(uint32_t* outJ, const uint32_t* xy, size_t n, int nt);
 void orc_to_affine(uint32_t* xy, const uint32_t* J, size_t n, int nt);
 /* y = sqrt(x^3-3x+b) per lane; ok[i] = 1 iff lane i is a square (the reference

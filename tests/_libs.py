@@ -211,3 +211,32 @@ QUIRK_FIELD = [0xA09D838E868B90F2B89CC416F270D3B8F0374E0A8728A79978B896A45AF4F8A
 EDGE_SCALARS = [0, 1, 2, 3, 4, 5, N_INT - 1, N_INT, N_INT + 1, 2**256 - 1, 2**256 - 2, 2**255, 2**255 + 1,
                 0x0BC1B1F28709DECB543D9677D2CC9942348F6B984DEFF409430740942FF38827,
                 0x0A891CEC7F6B6F8E0F2B3F6CC9F5E51D0B1A7C2BF6B3F3E7C4D5A6B7C8D9BD80]
+
+
+def quirk_stress(n, seed=1):
+    """Field elements in which one digit pair (i, j) is chosen so that a_i*a_j lies just
+    below 2^63 (high word 0x7fffffff): this is where the reference's square() can lose a
+    carry (include/ecsimd/mul.h:192-206).  Roughly a quarter of them really do."""
+    import random
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < n:
+        d = [rnd.getrandbits(32) for _ in range(8)]
+        i, j = sorted(rnd.sample(range(8), 2))
+        ai = rnd.getrandbits(32) | 0x80000000
+        aj = ((1 << 63) - 1 - rnd.getrandbits(20)) // ai
+        if aj >= 1 << 32:
+            continue
+        if rnd.random() < 0.5:
+            ai, aj = aj, ai
+        d[i], d[j] = ai, aj
+        if rnd.random() < 0.5:
+            # favour large neighbours so that ret[]/prev are large too
+            for k in range(8):
+                if k not in (i, j) and rnd.random() < 0.5:
+                    d[k] = 0xFFFFFFFF - rnd.getrandbits(8)
+        v = sum(x << (32 * k) for k, x in enumerate(d))
+        if v >= P_INT:
+            continue
+        out.append(v)
+    return to_words(out)
