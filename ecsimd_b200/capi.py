@@ -48,6 +48,8 @@ SYMBOLS = {
     "ecb200_to_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
     "ecb200_synth_values": (_i, [_vp, C.c_uint64, C.c_uint64, _i, _sz, _u32, _vp]),
     "ecb200_checksum": (_i, [_vp, _vp, _sz, _vp]),
+    "ecb200_microbench_mix": (_i, [_i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_float), _vp]),
+    "ecb200_microbench_mix_count": (_i, []),
     "ecb200_microbench": (_i, [_i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_float), _vp]),
 }
 

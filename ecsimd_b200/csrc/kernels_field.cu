@@ -230,6 +230,45 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t* __restrict__ out, 
   }
 }
 
+
+// Generic pipe-mix probe: per step NW x IMAD.WIDE.U32, NL x IMAD (lo), NH x IMAD.HI.U32 and
+// NA x (IADD3 + IADD3.X) pairs, every op on its own dependent chain (8 chains per kind).
+template <int NW, int NL, int NH, int NA>
+__global__ void __launch_bounds__(256) k_mix(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t wl[8], wh[8], l[8], h[8], al[8], ah[8];
+  const uint32_t y = in[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    wl[j] = in[j] + tid; wh[j] = ~wl[j]; l[j] = wl[j] * 3u; h[j] = wl[j] * 5u; al[j] = wl[j] * 7u; ah[j] = wl[j] * 9u;
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int j = 0; j < 12; j++) {
+        if (j < NW) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(wl[j & 7]), "+r"(wh[j & 7]) : "r"(wh[(j + 3) & 7]), "r"(y));
+        if (j < NL) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(l[j & 7]) : "r"(y), "r"(l[(j + 3) & 7]));
+        if (j < NH) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(h[j & 7]) : "r"(y), "r"(h[(j + 3) & 7]));
+        if (j < NA) asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(al[j & 7]), "+r"(ah[j & 7]) : "r"(ah[(j + 3) & 7]), "r"(al[(j + 5) & 7]));
+      }
+    }
+  }
+  uint32_t t = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) t += wl[j] ^ wh[j] ^ l[j] ^ h[j] ^ al[j] ^ ah[j];
+  out[tid] = t;
+}
+
+struct MixCombo { int nw, nl, nh, na; void (*fn)(uint32_t*, const uint32_t*, int); };
+#define MIX(a, b, c, d) {a, b, c, d, k_mix<a, b, c, d>}
+static const MixCombo g_mix[] = {
+    MIX(8, 0, 0, 0), MIX(0, 8, 0, 0), MIX(0, 0, 8, 0), MIX(0, 8, 8, 0), MIX(0, 0, 0, 8), MIX(8, 0, 0, 4), MIX(8, 0, 0, 8),
+    MIX(8, 0, 0, 12), MIX(0, 8, 8, 8), MIX(0, 8, 0, 8), MIX(0, 0, 8, 8), MIX(8, 8, 0, 0), MIX(8, 0, 8, 0), MIX(4, 8, 8, 8),
+    MIX(8, 4, 0, 8), MIX(8, 0, 4, 8), MIX(4, 0, 0, 12), MIX(0, 12, 0, 0), MIX(0, 12, 0, 12)};
+static const int g_nmix = (int)(sizeof(g_mix) / sizeof(g_mix[0]));
+
 template <int L, int OP, bool Q>
 static int launch_field(void* out, const void* a, const void* b, size_t n, int param, cudaStream_t s) {
   if (n == 0) return ECB200_OK;
@@ -474,5 +513,34 @@ int ecb200_microbench(int which, int blocks, int threads, int iters, double* ops
   *ops_per_iter = per[which];
   return ECB200_OK;
 }
+
+int ecb200_microbench_mix(int combo, int blocks, int threads, int iters, int* counts4, float* ms, void* stream) {
+  if (combo < 0 || combo >= g_nmix) { set_error("combo out of range (0..%d)", g_nmix - 1); return ECB200_ERR_ARG; }
+  if (blocks < 1 || threads < 32 || threads > 256 || iters < 1 || !counts4 || !ms) { set_error("bad argument"); return ECB200_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  void *din = nullptr, *dout = nullptr;
+  int rc;
+  if ((rc = sc.alloc(&din, 64))) return rc;
+  if ((rc = sc.alloc(&dout, (size_t)blocks * threads * 4))) return rc;
+  const uint32_t seedv[9] = {0x9e3779b9u, 0x7f4a7c15u, 0xf39cc060u, 0x5cedc834u, 0x1082276bu, 0xf3a27251u, 0xf86c6a11u, 0xd0c18e95u, 0x2767f0b1u};
+  ECB_CUDA(cudaMemcpyAsync(din, seedv, sizeof seedv, cudaMemcpyHostToDevice, s));
+  cudaEvent_t e0, e1;
+  ECB_CUDA(cudaEventCreate(&e0));
+  ECB_CUDA(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {
+    ECB_CUDA(cudaEventRecord(e0, s));
+    g_mix[combo].fn<<<blocks, threads, 0, s>>>((uint32_t*)dout, (const uint32_t*)din, iters);
+    ECB_LAUNCH_CHECK();
+    ECB_CUDA(cudaEventRecord(e1, s));
+    ECB_CUDA(cudaEventSynchronize(e1));
+  }
+  ECB_CUDA(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  counts4[0] = g_mix[combo].nw; counts4[1] = g_mix[combo].nl; counts4[2] = g_mix[combo].nh; counts4[3] = g_mix[combo].na;
+  return ECB200_OK;
+}
+int ecb200_microbench_mix_count(void) { return g_nmix; }
 
 }  // extern "C"

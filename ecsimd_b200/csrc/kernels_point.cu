@@ -6,6 +6,8 @@
 // kernels of kernels_field.cu.  The scalar multiplication is integer-multiply bound
 // (211 540 MAC32 per lane against 224 bytes of traffic), so the conversion passes are
 // noise there.
+#include <cstdlib>
+
 #include "host_common.cuh"
 #include "layout.cuh"
 #include "point.cuh"
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __
 
 // mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per lane
 // unless k_bcast (scalar_mult_1s: one scalar for all lanes).
-template <bool QUIRK, int MODE>
-__global__ void __launch_bounds__(128) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
+template <bool QUIRK, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
                                                      size_t n, int k_bcast) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -220,12 +222,21 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   if ((rc = st.out(out, 3, &dout))) return rc;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   const bool q = quirk_on(flags);
+  static const int minb = [] { const char* e = getenv("ECB200_SM_MINB"); return e ? atoi(e) : 3; }();
   if (mode == 0) {
-    if (q) k_scalar_mult<true, 0><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    else k_scalar_mult<false, 0><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    if (minb == 4) {
+      if (q) k_scalar_mult<true, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+      else k_scalar_mult<false, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    } else if (minb == 5) {
+      if (q) k_scalar_mult<true, 0, 5><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+      else k_scalar_mult<false, 0, 5><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    } else {
+      if (q) k_scalar_mult<true, 0, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+      else k_scalar_mult<false, 0, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    }
   } else {
-    if (q) k_scalar_mult<true, 1><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    else k_scalar_mult<false, 1><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    if (q) k_scalar_mult<true, 1, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    else k_scalar_mult<false, 1, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
   }
   ECB_LAUNCH_CHECK();
   return st.finish();

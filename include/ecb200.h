@@ -158,6 +158,12 @@ int ecb200_checksum(uint32_t* out8, const void* buf, size_t nwords, void* stream
  * elapsed milliseconds (CUDA events) in *ms. */
 int ecb200_microbench(int which, int blocks, int threads, int iters, double* ops_per_iter, float* ms, void* stream);
 
+/* Pipe-mix probe `combo` (0 .. ecb200_microbench_mix_count()-1): per step NW x IMAD.WIDE.U32,
+ * NL x IMAD, NH x IMAD.HI.U32, NA x (IADD3 + IADD3.X); 8 steps per loop trip.  counts4 receives
+ * {NW, NL, NH, NA}. */
+int ecb200_microbench_mix(int combo, int blocks, int threads, int iters, int* counts4, float* ms, void* stream);
+int ecb200_microbench_mix_count(void);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
