@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: batched variable-base P-256 scalar multiplication.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (ecb200_scalar_mult_p256 = the reference's
+scalar_mult_p256, lib/scalar_mult_p256.cpp:12-14) over one batch of 2^20 synthetic
+(scalar, point) pairs PER GPU (BASELINE.json configs[2]; weak scaling: lanes are
+independent, each rank owns an index range, no collective on the data path).
+
+`value`    device-resident throughput (inputs already in HBM, planar layout), scalar mults/s
+`e2e`      the same call through the C ABI with HOST buffers in the reference's pack
+           layout: H2D copy + layout conversion + kernel + conversion + D2H inside the timed region
+`roofline` integer-multiply roofline of the scalar-mult kernel: algorithmic MAC32 (211 540 per
+           lane = 2299 mul x 64 + 1789 sqr x 36) / CUDA-event kernel time, against
+           the IMAD.WIDE.U32 issue rate measured live on this GPU (ecb200_microbench)
+`cpu_baseline` the reference's own AVX2 code (oracle/_ref) on the box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LANES_PER_GPU = 1 << 20
+MAC32_PER_SCALAR_MULT = 2299 * 64 + 1789 * 36   # 211 540
+SEED_SCALARS, SEED_POINTS = 0xEC51D004, 0xEC51D003
+METRIC = "p256_scalar_mults_per_sec"
+UNIT = "scalar_mults/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=LANES_PER_GPU, help="lanes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- clocks during the timed region ---------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=10)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+# ---- CPU baselines (rank 0 only; checker libraries, never on the product path) ------------------
+def cpu_reference_rate(seconds_target, cores):
+    """ecsimd's own scalar_mult over 4-lane AVX2 packs (oracle/_ref, `kind: reference`), or the C
+    restatement (`kind: port`) when the compiled reference is not usable on this host."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import _libs
+    lib = _libs.reference(nt=cores)
+    kind = "reference"
+    if lib is None:
+        lib, kind = _libs.oracle(nt=cores), "port"
+    G = np.concatenate([_libs.to_words([_libs.GX_INT]), _libs.to_words([_libs.GY_INT])], axis=1)
+
+    def run(n):
+        GJ = lib.from_affine(np.repeat(G, n, axis=0))
+        k = _libs.raw256(SEED_SCALARS, n)
+        t0 = time.perf_counter()
+        lib.scalar_mult(k, GJ)
+        return time.perf_counter() - t0
+    n0 = 256 * cores
+    run(n0)                                   # warm-up (thread pool, page faults)
+    t = run(n0)
+    n = max(n0, int(n0 * seconds_target / max(t, 1e-6)) // (4 * cores) * (4 * cores))
+    t = run(n)
+    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d scalar mults (same seeded scalars, P=G), %.1f s, %d threads" % (n, t, cores)}, (lib, kind)
+
+
+def openssl_rate(cores, seconds=3.0):
+    exe = os.path.join(ROOT, "oracle", "_ref", "p256_openssl")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, str(cores), str(seconds)], capture_output=True, text=True, timeout=60).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import _libs
+    lib = _libs.reference(nt=cores)
+    kind = "reference"
+    if lib is None:
+        lib, kind = _libs.oracle(nt=cores), "port"
+    G = np.concatenate([_libs.to_words([_libs.GX_INT]), _libs.to_words([_libs.GY_INT])], axis=1)
+    # bounded sample per step: ~2 s of CPU work
+    n0 = 256 * cores
+    GJ = lib.from_affine(np.repeat(G, n0, axis=0))
+    k = _libs.raw256(SEED_SCALARS, n0)
+    lib.scalar_mult(k, GJ)
+    t0 = time.perf_counter(); lib.scalar_mult(k, GJ); t = time.perf_counter() - t0
+    n = max(n0, int(n0 * 2.0 / max(t, 1e-6)) // (4 * cores) * (4 * cores))
+    P = lib.from_affine(lib.to_affine(lib.scalar_mult(_libs.raw256(SEED_POINTS, n), lib.from_affine(np.repeat(G, n, axis=0)))))
+    k = _libs.raw256(SEED_SCALARS, n)
+    for _ in range(args.warmup):
+        lib.scalar_mult(k, P)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lib.scalar_mult(k, P)
+    el = time.perf_counter() - t0
+    value = n * args.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (u64 AVX2 lanes on the CPU)", "data": "synthetic",
+            "config": {"workload": "scalar_mult_p256 variable-base, bounded sample of %d (k,P) pairs per step on host cores" % n,
+                       "lanes_per_step": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d scalar mults per step x %d steps, %d threads" % (n, args.steps, cores)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import ecsimd_b200
+    from ecsimd_b200 import capi, device as dev, host, shard
+
+    rank, world, local = shard.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    ecsimd_b200.init(local)
+    cuda = torch.device("cuda", local)
+    n = args.lanes
+    lo = rank * n                                   # this rank's global index range [lo, lo + n)
+
+    # ---- synthetic inputs, generated on the device (not timed) --------------------------------
+    k = dev.synth_values(dev.empty(n, 1), SEED_SCALARS, lo, n, 0)
+    r = dev.synth_values(dev.empty(n, 1), SEED_POINTS, lo, n, 0)
+    J = dev.scalar_mult_base(dev.empty(n, 3), r, n)             # P_i = r_i * G
+    xy = dev.to_affine(dev.empty(n, 2), J, n)
+    P = dev.from_affine(dev.empty(n, 3), xy, n)                 # Montgomery (X, Y), Z = R
+    out = dev.empty(n, 3)
+    del J, r
+    torch.cuda.synchronize()
+
+    # ---- roofline denominator: IMAD.WIDE.U32 issue rate measured on this GPU, now -----------------
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    peak_wide = max(dev.microbench(0, sms * 32, 256, 2000)[0] for _ in range(3))   # MAC32/s
+
+    # ---- device-resident timed region -------------------------------------------------------------
+    step = lambda: dev.scalar_mult(out, k, P, n)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    shard.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ecsimd_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = ecsimd_b200.launch_count() - launches0
+    clocks = sampler.stop()
+    shard.barrier()
+    ms_local = e0.elapsed_time(e1)
+    ms = shard.max_over_ranks(ms_local, cuda if world > 1 else None)
+    lanes_total = shard.sum_over_ranks(n, cuda if world > 1 else None)
+    value = lanes_total * args.steps / (ms * 1e-3)
+    kernel_ms = ms_local / args.steps                      # one kernel launch per step on this path
+    achieved = n * MAC32_PER_SCALAR_MULT / (kernel_ms * 1e-3)
+
+    # ---- parity spot check against the CPU oracle (checker only; not timed) -------------------------
+    parity = "skipped"
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _libs
+            orc = _libs.oracle(nt=os.cpu_count() or 1)
+            m = 512
+            kk = host.soa_to_lane(k[:, :m].contiguous().cpu().numpy().view(np.uint32), 1)
+            PP = host.soa_to_lane(P[:, :m].contiguous().cpu().numpy().view(np.uint32), 3)
+            got = host.soa_to_lane(out[:, :m].contiguous().cpu().numpy().view(np.uint32), 3)
+            assert np.array_equal(kk, _libs.raw256(SEED_SCALARS, m, start=lo))
+            parity = "ok" if np.array_equal(got, orc.scalar_mult(kk, PP)) else "MISMATCH"
+        except Exception as ex:  # pragma: no cover
+            parity = "error: %r" % (ex,)
+
+    # ---- end to end through the C ABI with host buffers (reference pack layout) ---------------------
+    e2e_steps = max(1, min(args.steps, 4))
+    hk = torch.empty((n // 4, 32), dtype=torch.int32).pin_memory()
+    hP = torch.empty((n // 4, 96), dtype=torch.int32).pin_memory()
+    hout = torch.empty((n // 4, 96), dtype=torch.int32).pin_memory()
+    # same inputs, transposed on the host to the reference's pack layout (not timed)
+    hk.numpy().view(np.uint32)[:] = host.lane_to_pack4(host.soa_to_lane(k.cpu().numpy().view(np.uint32), 1), 1)
+    hP.numpy().view(np.uint32)[:] = host.lane_to_pack4(host.soa_to_lane(P.cpu().numpy().view(np.uint32), 3), 3)
+    flags_host = capi.LAYOUT_PACK4 | capi.MEM_HOST
+    hcall = lambda: capi.call("ecb200_scalar_mult_p256", hout.data_ptr(), hk.data_ptr(), hP.data_ptr(), n, flags_host, None)
+    hcall()
+    torch.cuda.synchronize()
+    shard.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hcall()                                              # synchronous: returns when hout is written
+    torch.cuda.synchronize()
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, cuda if world > 1 else None)
+    e2e_value = lanes_total * e2e_steps / e2e_s
+    e2e_ok = None
+    if rank == 0 and parity == "ok":
+        got = host.pack4_to_lane(hout[:128].numpy().view(np.uint32), 3)
+        e2e_ok = bool(np.array_equal(got, host.soa_to_lane(out[:, :512].contiguous().cpu().numpy().view(np.uint32), 3)))
+
+    # ---- secondary kernels of the path (config 1): streaming mulmod and register-resident mulmod ---------
+    aux = {}
+    if rank == 0:
+        a = dev.synth_values(dev.empty(n, 1), 0xEC51D001, 0, n, 1)
+        b = dev.synth_values(dev.empty(n, 1), 0xEC51D002, 0, n, 1)
+        o1 = dev.empty(n, 1)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+
+        def timed(fn, reps):
+            best = 1e30
+            for _ in range(reps):
+                flush.zero_()                                  # evict L2 between timed iterations
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(); fn(); s1.record(); torch.cuda.synchronize()
+                best = min(best, s0.elapsed_time(s1))
+            return best
+        dev.mgry_mul(o1, a, b, n); torch.cuda.synchronize()
+        t_mul = timed(lambda: dev.mgry_mul(o1, a, b, n), 5)
+        t_chain = timed(lambda: dev.mgry_mul_chain(o1, a, b, 1024, n), 2)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        aux = {"mulmod_stream": {"lanes": n, "ms": t_mul, "mulmod_per_s": n / t_mul * 1e3, "achieved_GBps": n * 96 / t_mul * 1e3 / 1e9,
+                                 "hbm_peak_GBps": hbm_peak, "frac_of_%s" % ("measured" if "hbm_gbs" in peaks else "fallback"): n * 96 / t_mul * 1e3 / 1e9 / hbm_peak,
+                                 "note": "2^20 lanes = 96 MiB of traffic: fits the 126 MB L2 even after the flush of the inputs' lines; see profiles/ for dram bytes"},
+               "mulmod_register_resident": {"mulmod_per_s": n * 1024 / t_chain * 1e3, "TMAC32_per_s": n * 1024 * 64 / t_chain * 1e3 / 1e12,
+                                            "frac_of_imad_peak": n * 1024 * 64 / t_chain * 1e3 / peak_wide}}
+        del a, b, o1, flush
+
+    if rank != 0:
+        return 0
+
+    cpu = None
+    p256_ref = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu, _ = cpu_reference_rate(12.0, cores)
+        p256_ref = openssl_rate(cores)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "scalar_mult_p256 variable-base, 2^%d (k,P) pairs per GPU per step (BASELINE configs[2])" % (n.bit_length() - 1),
+                   "lanes_per_gpu": n, "layout": "SOA planes in HBM", "parallelism": "index-range shards, no collective",
+                   "l2": "inputs+outputs per step = %d MiB > 126 MB L2" % (n * 224 >> 20), "quirk_exact": True},
+        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "TMAC32/s", "frac": achieved / peak_wide,
+                     "traffic": None, "kernel": "k_scalar_mult", "kernel_ms": kernel_ms,
+                     "peak_source": "IMAD.WIDE.U32 rate measured live by ecb200_microbench on this GPU (not in MEASURED_PEAKS.json)",
+                     "algorithmic_mac32_per_lane": MAC32_PER_SCALAR_MULT},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128 * world, "d2h_bytes_per_step": n * 96 * world,
+                "steps": e2e_steps, "layout": "reference pack4, pinned host buffers", "matches_device_path": e2e_ok},
+        "gpu_launches": launches, "clocks": clocks, "parity_vs_oracle": parity, "aux": aux,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    if p256_ref:
+        line["p256_ref_openssl"] = p256_ref
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
