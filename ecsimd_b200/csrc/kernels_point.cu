@@ -68,6 +68,31 @@ __global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __
 // unless k_bcast (scalar_mult_1s: one scalar for all lanes).
 template <bool QUIRK, int MODE, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
+                                                     size_t n, int k_bcast);
+
+// One block of 384 threads per SM (12 warps), all warps kept in step by a barrier per ladder
+// iteration: the ~60 KB loop body is then fetched once per SM instead of once per warp.
+template <bool QUIRK, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restrict__ out, const void* __restrict__ k,
+                                                                 const void* __restrict__ P, size_t n, int k_bcast) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = i0 < n ? i0 : n - 1;  // surplus threads recompute the last lane (they must reach the barriers)
+  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : S::load(k, n, i, 1, 0);
+  fe px, py;
+  if (MODE == 0) {
+    px = S::load(P, n, i, 3, 0);
+    py = S::load(P, n, i, 3, 1);
+  } else {
+    const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
+    px = fe_const(gx);
+    py = fe_const(gy);
+  }
+  const jac r = pt_scalar_mult<QUIRK, true>(kk.v, px, py);
+  if (i0 < n) store_jac(out, n, i, r);
+}
+
+template <bool QUIRK, int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
                                                      size_t n, int k_bcast) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -223,7 +248,16 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   const unsigned blocks = (unsigned)((n + 127) / 128);
   const bool q = quirk_on(flags);
   static const int minb = [] { const char* e = getenv("ECB200_SM_MINB"); return e ? atoi(e) : 3; }();
-  if (mode == 0) {
+  if (mode == 0 && minb >= 384) {
+    const unsigned b2 = (unsigned)((n + minb - 1) / minb);
+    if (minb == 384) {
+      if (q) k_scalar_mult_sync<true, 0, 384><<<b2, 384, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+      else k_scalar_mult_sync<false, 0, 384><<<b2, 384, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    } else {
+      if (q) k_scalar_mult_sync<true, 0, 512><<<b2, 512, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+      else k_scalar_mult_sync<false, 0, 512><<<b2, 512, 0, st.s>>>(dout, dk, dP, n, k_bcast);
+    }
+  } else if (mode == 0) {
     if (minb == 4) {
       if (q) k_scalar_mult<true, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
       else k_scalar_mult<false, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);

@@ -136,7 +136,9 @@ __device__ __forceinline__ jac pt_trplu(jac& P) {
 // scalar (never reduced mod the group order).  The two masked swaps per step of the
 // reference (swap.h:47-56) bracket each ZDAU; the closing swap of step b and the
 // opening swap of step b+1 are merged into one swap on (bit_b xor bit_{b+1}).
-template <bool QUIRK>
+// SYNC: all warps of the block meet at a barrier once per ladder step, so that they walk
+// the (large, fully unrolled) loop body together and share instruction-cache lines.
+template <bool QUIRK, bool SYNC = false>
 __device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& Px, const fe& Py) {
   jac P;
   P.x = Px; P.y = Py; P.z = fe_R();
@@ -153,6 +155,7 @@ __device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& 
     fe_cswap(sw, P.y, base.y);
     pt_zdau_xy<QUIRK>(base.x, base.y, P.x, P.y, Z);
     prev = bit;
+    if (SYNC) __syncthreads();
   }
   fe_cswap(prev, P.x, base.x);
   fe_cswap(prev, P.y, base.y);
