@@ -71,19 +71,29 @@ __device__ __forceinline__ fe fp_sub(const fe& a, const fe& b) {
   return d;
 }
 
-// s (with carry-out c): return s if (s - p borrows and c == 0) else s - p
+// t_lo >= p, for the rare case t7 == 0xffffffff (p = ffffffff 00000001 00000000 00000000 00000000 ffffffff ffffffff ffffffff)
+static __device__ __noinline__ uint32_t fp_ge_p_rare(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5, uint32_t t6) {
+  if (t6 != 1u) return t6 > 1u;
+  if ((t3 | t4 | t5) != 0u) return 1u;
+  return (t0 & t1 & t2) == 0xffffffffu;
+}
+
+// The single conditional subtraction every modular op ends with (sub_if_above, sub.h:46-69):
+// given the 257-bit value (c:s), return it minus p if it is >= p.  c == 1 always subtracts;
+// c == 0 subtracts only if s >= p, which needs s7 == 0xffffffff (probability 2^-32 on uniform
+// data): that case branches to an exact comparison, everything else is one 8-word add of
+// (2^256 - p) & mask = {sub, 0, 0, mask, mask, mask, mask<<1, 0}.
 __device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c) {
-  fe d;
-  uint32_t bw;
-  asm("sub.cc.u32 %0, %9, 0xffffffff; subc.cc.u32 %1, %10, 0xffffffff; subc.cc.u32 %2, %11, 0xffffffff; subc.cc.u32 %3, %12, 0; "
-      "subc.cc.u32 %4, %13, 0; subc.cc.u32 %5, %14, 0; subc.cc.u32 %6, %15, 1; subc.cc.u32 %7, %16, 0xffffffff; "
-      "subc.u32 %8, 0, 0;"
-      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]), "=r"(bw)
-      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]));
-  const bool keep = (bw != 0u) && (c == 0u);
+  uint32_t sub = c;
+  if (__builtin_expect(s.v[7] == 0xffffffffu && c == 0u, 0))
+    sub = fp_ge_p_rare(s.v[0], s.v[1], s.v[2], s.v[3], s.v[4], s.v[5], s.v[6]);
+  const uint32_t mask = 0u - sub, k6 = mask + mask;
   fe r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = keep ? s.v[i] : d.v[i];
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, 0; addc.cc.u32 %2, %10, 0; addc.cc.u32 %3, %11, %17; "
+      "addc.cc.u32 %4, %12, %17; addc.cc.u32 %5, %13, %17; addc.cc.u32 %6, %14, %18; addc.u32 %7, %15, 0;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+        "r"(sub), "r"(mask), "r"(k6));
   return r;
 }
 
@@ -116,11 +126,12 @@ __device__ __forceinline__ fe fp_shl(const fe& a) {
 }
 
 __device__ __forceinline__ fe fp_mul(const fe& a, const fe& b) {
-  fe r;
-  fp_mul_words(r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7],
-               a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
-               b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6], b.v[7]);
-  return r;
+  fe t;
+  uint32_t t8;
+  fp_mul_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8,
+            a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
+            b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6], b.v[7]);
+  return fp_reduce_once(t, t8);
 }
 
 // ---- squaring ------------------------------------------------------------------------
@@ -132,10 +143,9 @@ __device__ __forceinline__ fe fp_mul(const fe& a, const fe& b) {
 // A wrap needs 2*pr mod 2^64 >= 2^64 - 2^33 - 1 for some cross product
 // pr = a_i*a_j (the other two addends are < 2^32+2 and <= 2^32), i.e. bit 63 of
 // pr clear and bits 62..32 all set: the high word of pr, read as a signed int,
-// is INT_MAX.  So: fast path = true square (the multiplier above), plus a
-// 3-input signed max over the 28 cross-product high words; only if that max is
-// INT_MAX (probability ~ 6.5e-9 per lane) the lane re-runs the reference's loop
-// literally (fp_sqr_quirk_slow).
+// is INT_MAX.  So: fast path = true square (fp_sqr_t9) plus a cheap necessary-condition
+// filter (fp_sqr_quirk_filter below); only lanes that pass it AND the exact test
+// (probability ~ 6.5e-9 per lane) re-run the reference's loop literally (fp_sqr_quirk_slow).
 static __device__ __noinline__ void fp_sqr_quirk_slow(uint32_t* r, const uint32_t* a) {
   // literal restatement of mul.h:176-210 on 64-bit wrap-around integers
   unsigned long long ret[17];
@@ -185,31 +195,54 @@ static __device__ __noinline__ void fp_sqr_quirk_slow(uint32_t* r, const uint32_
   for (int k = 0; k < 8; k++) r[k] = lt ? (uint32_t)acc[8 + k] : d[k];
 }
 
-__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a) {
+// exact test: is some cross-product high word 0x7fffffff (INT_MAX as a signed int)?
+static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t* a) {
   int m = 0;
+  for (int i = 0; i < 7; i++)
+    for (int j = i + 1; j < 8; j++) m = max(m, (int)__umulhi(a[i], a[j]));
+  return (uint32_t)m == 0x7fffffffu;
+}
+
+// First-level filter on the FMA pipe's cheap 32-bit IMAD (2 clk/warp against 5 for IMAD.HI):
+// with A = a_i >> 16, B = a_j >> 16 we have A*B*2^32 <= a_i*a_j < (A*B + A + B + 1)*2^32, so
+// hi32(a_i*a_j) == 0x7fffffff forces A*B into [0x7ffe0000, 0x7fffffff], i.e.
+// (A*B + 0x80020000) mod 2^32 < 0x20000.  An unsigned 3-input min over the 28 products keeps it
+// to one IMAD + half a VIMNMX3 per cross product.  False-positive rate ~ 28 * 2^-15 per lane,
+// resolved by the exact test above; real hits (~6.5e-9 per lane) take the slow path.
+__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a) {
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) h[i] = a.v[i] >> 16;
+  uint32_t m = 0xffffffffu;
 #pragma unroll
   for (int i = 0; i < 7; i++) {
 #pragma unroll
     for (int j = i + 1; j < 8; j += 2) {
-      const int h0 = (int)__umulhi(a.v[i], a.v[j]);
-      const int h1 = (j + 1 < 8) ? (int)__umulhi(a.v[i], a.v[j + 1]) : 0;
-      m = __vimax3_s32(m, h0, h1);
+      const uint32_t y0 = h[i] * h[j] + 0x80020000u;
+      const uint32_t y1 = (j + 1 < 8) ? h[i] * h[j + 1] + 0x80020000u : 0xffffffffu;
+      m = __vimin3_u32(m, y0, y1);
     }
   }
-  return (uint32_t)m;
+  return m;
 }
 
 template <bool QUIRK = true>
 __device__ __forceinline__ fe fp_sqr(const fe& a) {
-  fe r = fp_mul(a, a);
+  fe t;
+  uint32_t t8;
+  fp_sqr_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8,
+            a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7]);
+  fe r = fp_reduce_once(t, t8);
   if (QUIRK) {
-    if (fp_sqr_quirk_filter(a) == 0x7fffffffu) {
+    if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
       uint32_t in[8], out[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
-      fp_sqr_quirk_slow(out, in);
+      if (fp_sqr_quirk_filter_exact(in)) {
+        fp_sqr_quirk_slow(out, in);
 #pragma unroll
-      for (int i = 0; i < 8; i++) r.v[i] = out[i];
+        for (int i = 0; i < 8; i++) r.v[i] = out[i];
+      }
     }
   }
   return r;

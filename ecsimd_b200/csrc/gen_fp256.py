@@ -124,6 +124,30 @@ class Emit:
             self.line("addc.u32 {0}, {0}, 0;", (d, "rw"))
         self.ir.append(("cap", d, fresh))
 
+    def capb(self, d):
+        """d = 0 - 0 - borrow  (0 or 0xffffffff)"""
+        self.line("subc.u32 {0}, 0, 0;", (d, "w"))
+        self.ir.append(("capb", d))
+
+    def setc(self, c):
+        """carry flag := (c != 0) for c in {0,1}"""
+        self.line("add.cc.u32 {0}, {1}, 0xffffffff;", ("scratch", "w"), (c, "r"))
+        self.ir.append(("setc", c))
+
+    def setb(self, b):
+        """borrow flag := (b != 0) for b in {0, 0xffffffff}"""
+        self.line("sub.cc.u32 {0}, 0, {1};", ("scratch", "w"), (b, "r"))
+        self.ir.append(("setb", b))
+
+    def shl32(self, d, a, n):
+        self.line("shl.b32 {0}, {1}, %d;" % n, (d, "w"), (a, "r"))
+        self.ir.append(("shl32", d, a, n))
+
+    def shf_l(self, d, lo, hi, n):
+        """d = (hi:lo) << n, upper word (funnel shift)"""
+        self.line("shf.l.clamp.b32 {0}, {1}, {2}, %d;" % n, (d, "w"), (lo, "r"), (hi, "r"))
+        self.ir.append(("shf_l", d, lo, hi, n))
+
     def and32(self, d, a, imm):
         self.line("and.b32 {0}, {1}, %d;" % imm, (d, "w"), (a, "r"))
         self.ir.append(("and32", d, a, imm))
@@ -196,6 +220,8 @@ def simulate(ir, env):
             if cin:
                 assert cc is not None
             t = val(a) - val(b) - (cc if cin else 0)
+            if not cout:
+                assert t >= 0, "lost borrow in sub32 %s" % (ins,)
             env[d] = t & M32
             cc = 1 if t < 0 else 0   # CC.CF holds the borrow for sub
         elif k == "cap":
@@ -208,192 +234,333 @@ def simulate(ir, env):
         elif k == "and32":
             _, d, a, imm = ins
             env[d] = val(a) & imm
+        elif k == "capb":
+            assert cc is not None
+            env[ins[1]] = M32 if cc else 0
+            cc = None
+        elif k == "setc":
+            assert val(ins[1]) in (0, 1)
+            cc = val(ins[1])
+        elif k == "setb":
+            assert val(ins[1]) in (0, M32)
+            cc = 1 if val(ins[1]) else 0
+        elif k == "shl32":
+            _, d, a, n = ins
+            env[d] = (val(a) << n) & M32
+        elif k == "shf_l":
+            _, d, lo, hi, n = ins
+            env[d] = (((val(hi) << 32) | val(lo)) << n >> 32) & M32
         else:
             raise ValueError(k)
     return env
 
 
-def gen_mul(final="canonical"):
-    """CIOS Montgomery product in E/O form.  Absolute word positions: E pair at
-    even w is (e{w}, e{w+1}); O pair at odd w is (o{w}, o{w+1})."""
-    g = Emit()
-    touched = set()      # registers that hold a value (not fresh)
+# ---------------------------------------------------------------------------------------------
+# Schedules.  Absolute word positions: the E accumulator holds pairs at even positions
+# (e{w}, e{w+1}), the O accumulator pairs at odd positions (o{w}, o{w+1}).  A "chain" is a
+# list of (position, x, y) products at strictly ascending consecutive pairs of ONE accumulator;
+# the carry travels from one multiply-add to the next in a predicate.  A chain may end without
+# capturing its carry only where the carry cannot exist: on a pair nothing has touched yet
+# (a*b + carry < 2^64) or on the top pair of the accumulator (the whole sum is bounded).
+# Every 32x32+64 step is one IMAD.WIDE.U32(.X): 4.1 clk of the FMA-heavy pipe per warp on B200
+# (measured, tools/microbench_mix.py), so the schedules below use exactly 64 (mul) / 36 (sqr)
+# of them and keep everything else on plain IADD3 carry chains.
+MUL_E_CHAINS = [
+    [(0, 0, 0), (2, 0, 2), (4, 0, 4), (6, 0, 6)],
+    [(2, 2, 0), (4, 2, 2), (6, 2, 4), (8, 2, 6)],
+    [(2, 1, 1), (4, 1, 3), (6, 1, 5), (8, 1, 7), (10, 3, 7)],
+    [(4, 4, 0), (6, 4, 2), (8, 4, 4), (10, 4, 6), (12, 5, 7)],
+    [(4, 3, 1), (6, 3, 3), (8, 3, 5), (10, 5, 5), (12, 6, 6), (14, 7, 7)],
+    [(6, 6, 0), (8, 6, 2), (10, 6, 4), (12, 7, 5)],
+    [(6, 5, 1), (8, 5, 3), (10, 7, 3)],
+    [(8, 7, 1)],
+]
+MUL_O_CHAINS = [
+    [(1, 0, 1), (3, 0, 3), (5, 0, 5), (7, 0, 7)],
+    [(1, 1, 0), (3, 1, 2), (5, 1, 4), (7, 1, 6), (9, 3, 6)],
+    [(3, 2, 1), (5, 2, 3), (7, 2, 5), (9, 2, 7), (11, 4, 7)],
+    [(3, 3, 0), (5, 3, 2), (7, 3, 4), (9, 5, 4), (11, 5, 6), (13, 7, 6)],
+    [(5, 4, 1), (7, 4, 3), (9, 4, 5), (11, 6, 5), (13, 6, 7)],
+    [(5, 5, 0), (7, 5, 2), (9, 7, 2), (11, 7, 4)],
+    [(7, 6, 1), (9, 6, 3)],
+    [(7, 7, 0)],
+]
+# cross products a_i*a_j, i<j, of the squaring
+SQR_E_CHAINS = [
+    [(2, 0, 2), (4, 0, 4), (6, 0, 6), (8, 1, 7)],
+    [(4, 1, 3), (6, 1, 5), (8, 2, 6), (10, 3, 7)],
+    [(6, 2, 4), (8, 3, 5), (10, 4, 6), (12, 5, 7)],
+]
+SQR_O_CHAINS = [
+    [(1, 0, 1), (3, 0, 3), (5, 0, 5), (7, 0, 7)],
+    [(3, 1, 2), (5, 1, 4), (7, 1, 6), (9, 2, 7)],
+    [(5, 2, 3), (7, 2, 5), (9, 3, 6), (11, 4, 7)],
+    [(7, 3, 4), (9, 4, 5), (11, 5, 6), (13, 6, 7)],
+]
+
+
+def _check_cover(chains_e, chains_o, square):
+    seen = set()
+    for acc, chains in (("e", chains_e), ("o", chains_o)):
+        for ch in chains:
+            prev = None
+            for (w, i, j) in ch:
+                assert w == i + j and (w % 2 == 0) == (acc == "e")
+                assert prev is None or w == prev + 2
+                assert (i, j) not in seen
+                seen.add((i, j))
+                prev = w
+    want = {(i, j) for i in range(8) for j in range(8) if (i < j if square else True)}
+    assert seen == want, (sorted(want - seen), sorted(seen - want))
+
+
+def emit_products(g, chains_e, chains_o, xa, xb, tops):
+    """Emit the product chains.  Returns (touched registers, captured carry words {position: [regs]})."""
+    touched = set()
+    caps = {}
 
     def R(acc, w):
         return "%s%d" % (acc, w)
+    for acc, chains in (("e", chains_e), ("o", chains_o)):
+        top = tops[acc]
+        for ch in chains:
+            allfresh = all(R(acc, w) not in touched and R(acc, w + 1) not in touched for (w, _, _) in ch)
+            g.begin()
+            cin = False
+            for n, (w, i, j) in enumerate(ch):
+                lo, hi = R(acc, w), R(acc, w + 1)
+                last = n == len(ch) - 1
+                fresh = (lo not in touched, hi not in touched)
+                if allfresh:
+                    g.mulw(lo, hi, xa % i, xb % j)
+                else:
+                    # the carry out of the last step is dropped only where it cannot exist
+                    safe_end = last and (all(fresh) or w == top)
+                    g.madw(lo, hi, xa % i, xb % j, cin, not safe_end, fresh=fresh)
+                    cin = True
+                    if last and not safe_end:
+                        c = "c%s%d" % (acc, w + 2)
+                        g.cap(c, True)
+                        caps.setdefault(w + 2, []).append(c)
+                touched.add(lo); touched.add(hi)
+            g.end()
+    return touched, caps
 
-    def pair_fresh(acc, w):
-        return R(acc, w) not in touched and R(acc, w + 1) not in touched
 
-    def wfresh(acc, w):
-        return (R(acc, w) not in touched, R(acc, w + 1) not in touched)
-
-    def touch(acc, w):
-        touched.add(R(acc, w)); touched.add(R(acc, w + 1))
-
-    for i in range(8):
-        Pn, Qn = ("e", "o") if i % 2 == 0 else ("o", "e")   # P has the parity of i
-        b = "b%d" % i
-        # ---- Q chain: [transfer] + odd-k products at words i+k ---------------
-        g.begin()
-        cin = False
-        if i > 0:
-            # word i lives in P (low word of pair (i,i+1)) and in Q (high word of pair (i-1,i))
-            g.add32(R(Pn, i), R(Pn, i), R(Qn, i), False, True)
-            cin = True
-        for k in (1, 3, 5, 7):
-            w = i + k
-            last = k == 7
-            if pair_fresh(Qn, w) and not cin:
-                g.mulw(R(Qn, w), R(Qn, w + 1), "a%d" % k, b)
-                cin = False
-            else:
-                fr = wfresh(Qn, w)
-                g.madw(R(Qn, w), R(Qn, w + 1), "a%d" % k, b, cin, not last, fresh=fr)
-                cin = not last
-            touch(Qn, w)
-        g.end()
-        # ---- P chain: even-k products --------------------------------------------
-        g.begin()
-        cin = False
-        allfresh = all(pair_fresh(Pn, i + k) for k in (0, 2, 4, 6))
-        for k in (0, 2, 4, 6):
-            w = i + k
-            if allfresh:
-                g.mulw(R(Pn, w), R(Pn, w + 1), "a%d" % k, b)
-            else:
-                fr = wfresh(Pn, w)
-                g.madw(R(Pn, w), R(Pn, w + 1), "a%d" % k, b, cin, True, fresh=fr)
-                cin = True
-            touch(Pn, w)
-        if not allfresh:
-            top = R(Pn, i + 8)
-            g.cap(top, top not in touched)
-            touched.add(top)
-        g.end()
-        m = R(Pn, i)
-        # ---- reduction, Q side: m@i+3, ripple@i+5, m*0xffffffff@i+7 -----------------
-        g.begin()
-        g.madw(R(Qn, i + 3), R(Qn, i + 4), m, 1, False, True, fresh=wfresh(Qn, i + 3))
-        g.addw(R(Qn, i + 5), R(Qn, i + 6), True, True)
-        g.madw(R(Qn, i + 7), R(Qn, i + 8), m, 0xFFFFFFFF, True, True, fresh=wfresh(Qn, i + 7))
-        top = R(Qn, i + 9)
-        g.cap(top, top not in touched)
-        touched.add(top)
-        g.end()
-        # ---- reduction, P side: m@i+6 ------------------------------------------------
-        g.begin()
-        g.madw(R(Pn, i + 6), R(Pn, i + 7), m, 1, False, True, fresh=wfresh(Pn, i + 6))
-        top = R(Pn, i + 8)
-        g.cap(top, top not in touched)
-        touched.add(top)
-        g.end()
-    # ---- merge t = E[8..16] + O[8..16] ------------------------------------------------
+def emit_reduction(g, T):
+    """Montgomery reduction of the 16-word T (register names T[0..15]) for p256, on plain carry
+    chains.  m = -T/p mod 2^256 is found word by word (m' = 1) from
+        m = low256(T + (m<<96) + (m<<192) - (m<<224))
+    and the quotient is t = (T + (m<<96) + (m<<192) - (m<<224) + (m<<256)) >> 256, nine words
+    h0..h8 (h8 is 0 or 1); the conditional subtraction of p is left to the caller."""
+    m = ["%s" % T[0], "%s" % T[1], "%s" % T[2], "m3", "m4", "m5", "m6", "m7"]
+    # low words of +(m<<192) and -(m<<224): they need only m0, m1
     g.begin()
-    for w in range(8, 17):
-        ew, ow = R("e", w), R("o", w)
-        ev = ew if ew in touched else 0
-        ov = ow if ow in touched else 0
-        g.add32("t%d" % (w - 8), ev, ov, w > 8, w < 16)
+    g.add32("x6", T[6], m[0], False, True)
+    g.add32("x7", T[7], m[1], True, True)
+    g.cap("cB", True)
     g.end()
-    if final == "canonical":
-        # d = t - p (9 words); mask = all-ones iff t < p; r = d + (p & mask)
-        pw = [(P >> (32 * k)) & M32 for k in range(8)]
-        g.begin()
-        for k in range(8):
-            g.sub32("d%d" % k, "t%d" % k, pw[k], k > 0, True)
-        g.sub32("mk", "t8", 0, True, False)
-        g.end()
-        g.begin()
-        g.and32("m1", "mk", 1)
-        g.end()
-        g.begin()
-        addp = ["mk", "mk", "mk", 0, 0, 0, "m1", "mk"]
-        for k in range(8):
-            g.add32("r%d" % k, "d%d" % k, addp[k], k > 0, k < 7, wrap_ok=True)  # mod 2^256
-        g.end()
-    return g, touched
+    g.begin()
+    g.sub32("y7", "x7", m[0], False, True)
+    g.capb("bC")
+    g.end()
+    # +(m<<96): words 3..7 give m3..m7, and the same chain runs on through the high half
+    g.begin()
+    g.add32("m3", T[3], m[0], False, True)
+    g.add32("m4", T[4], m[1], True, True)
+    g.add32("m5", T[5], m[2], True, True)
+    g.add32("m6", "x6", "m3", True, True)
+    g.add32("m7", "y7", "m4", True, True)
+    for k in range(8):
+        src = m[5 + k] if 5 + k < 8 else 0
+        g.add32("h%d" % k, T[8 + k], src, True, True)
+    g.cap("h8", True)
+    g.end()
+    # +(m<<192), high half: m2..m7 at h0..h5, carry-in = cB
+    g.begin()
+    g.setc("cB")
+    for k in range(8):
+        src = m[2 + k] if 2 + k < 8 else 0
+        g.add32("h%d" % k, "h%d" % k, src, True, True)
+    g.cap("h8", False)
+    g.end()
+    # +(m<<256): m0..m7 at h0..h7
+    g.begin()
+    for k in range(8):
+        g.add32("h%d" % k, "h%d" % k, m[k], k > 0, True)
+    g.cap("h8", False)
+    g.end()
+    # -(m<<224), high half: m1..m7 at h0..h6, borrow-in = bC
+    g.begin()
+    g.setb("bC")
+    for k in range(8):
+        src = m[1 + k] if 1 + k < 8 else 0
+        g.sub32("h%d" % k, "h%d" % k, src, True, True)
+    g.sub32("h8", "h8", 0, True, False)
+    g.end()
 
 
-def check(g, ntests=3000, seed=1):
+def gen_mul():
+    _check_cover(MUL_E_CHAINS, MUL_O_CHAINS, False)
+    g = Emit()
+    touched, caps = emit_products(g, MUL_E_CHAINS, MUL_O_CHAINS, "a%d", "b%d", {"e": 14, "o": None})
+    # merge T = E + O (word 0 is e0 itself)
+    g.begin()
+    for w in range(1, 16):
+        ev = "e%d" % w if "e%d" % w in touched else 0
+        ov = "o%d" % w if "o%d" % w in touched else 0
+        g.add32("t%d" % w, ev, ov, w > 1, w < 15)
+    g.end()
+    # the carries captured at chain ends
+    lo = min(caps)
+    g.begin()
+    first = True
+    for w in range(lo, 16):
+        cs = caps.get(w, [])
+        assert len(cs) <= 1
+        g.add32("t%d" % w, "t%d" % w, cs[0] if cs else 0, not first, w < 15)
+        first = False
+    g.end()
+    emit_reduction(g, ["e0"] + ["t%d" % w for w in range(1, 16)])
+    return g
+
+
+def gen_sqr():
+    _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
+    g = Emit()
+    touched, caps = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None})
+    assert not caps
+    # cross sum S = E + O: words 1..14, carry into word 15
+    g.begin()
+    for w in range(1, 15):
+        ev = "e%d" % w if "e%d" % w in touched else 0
+        ov = "o%d" % w if "o%d" % w in touched else 0
+        if ev == 0 and ov == 0:
+            continue
+        g.add32("s%d" % w, ev, ov, w > 1, True)
+    g.cap("s15", True)
+    g.end()
+    # doubled: d = 2*S (words 1..15; bit 0 of word 1 is zero)
+    g.begin()
+    g.shl32("d1", "s1", 1)
+    for w in range(2, 16):
+        g.shf_l("d%d" % w, "s%d" % (w - 1), "s%d" % w, 1)
+    g.end()
+    # T = d + sum a_i^2 2^(64 i): one chain of eight multiply-adds on the pairs (2i, 2i+1)
+    g.begin()
+    g.mulw("t0", "t1x", "a0", "a0")
+    g.add32("t1", "t1x", "d1", False, True)
+    for i in range(1, 8):
+        g.madw("d%d" % (2 * i), "d%d" % (2 * i + 1), "a%d" % i, "a%d" % i, True, i < 7)
+    g.end()
+    T = ["t0", "t1"] + ["d%d" % w for w in range(2, 16)]
+    emit_reduction(g, T)
+    return g
+
+
+def _cases(ntests, seed, unary):
     rnd = random.Random(seed)
     specials = [0, 1, P - 1, P - 2, 2**256 - 1, 2**255, 2**224 - 1, M32, (2**256 - 1) ^ (M32 << 96),
                 int("ffffffff" * 8, 16), int("80000000" * 8, 16), int("7fffffff" * 8, 16),
                 int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16), 2**96 - 1, 2**192, P >> 1]
-    cases = [(x, y) for x in specials for y in specials]
+    cases = [(x, x) for x in specials] if unary else [(x, y) for x in specials for y in specials]
+
+    def pattern():
+        return int("".join(rnd.choice(["ffffffff", "00000000", "%08x" % rnd.getrandbits(32)]) for _ in range(8)), 16)
     for _ in range(ntests):
-        bits = rnd.choice([256, 256, 256, 255, 200, 64])
-        x = rnd.getrandbits(bits); y = rnd.getrandbits(rnd.choice([256, 256, 224, 32]))
-        if rnd.random() < 0.2:
-            # words of all-ones / all-zeros patterns stress the carry paths
-            x = int("".join(rnd.choice(["ffffffff", "00000000", "%08x" % rnd.getrandbits(32)]) for _ in range(8)), 16)
-            y = int("".join(rnd.choice(["ffffffff", "00000000", "%08x" % rnd.getrandbits(32)]) for _ in range(8)), 16)
-        cases.append((x, y))
-    Rinv = pow(2**256, -1, P)
+        x = rnd.getrandbits(rnd.choice([256, 256, 256, 255, 200, 64]))
+        y = rnd.getrandbits(rnd.choice([256, 256, 224, 32]))
+        if rnd.random() < 0.25:      # words of all-ones / all-zeros stress the carry paths
+            x, y = pattern(), pattern()
+        cases.append((x, x) if unary else (x, y))
+    return cases
+
+
+def check(g, unary=False, ntests=3000, seed=1):
+    """Simulate the emitted PTX on edge and random operands (ANY 256-bit pattern, not only
+    canonical ones) and compare the nine-word quotient with the exact value."""
+    pinv = pow(P, -1, 2**256)
+    cases = _cases(ntests, seed, unary)
     for x, y in cases:
         env = {}
         for k in range(8):
             env["a%d" % k] = (x >> (32 * k)) & M32
             env["b%d" % k] = (y >> (32 * k)) & M32
         simulate(g.ir, env)
-        r = sum(env["r%d" % k] << (32 * k) for k in range(8))
+        got = sum(env["h%d" % k] << (32 * k) for k in range(9))
         T = x * y
-        m = (-T * pow(P, -1, 2**256)) % 2**256
-        t = (T + m * P) >> 256
-        want = t - P if t >= P else t
-        want &= 2**256 - 1
-        assert r == want, "mismatch for %x * %x: got %x want %x" % (x, y, r, want)
-        if x < P and y < P:
-            assert r == (x * y * Rinv) % P
+        m = (-T * pinv) % 2**256
+        want = (T + m * P) >> 256
+        assert got == want, "mismatch for %x * %x: got %x want %x" % (x, y, got, want)
     return len(cases)
 
 
-HEADER = '''// GENERATED by gen_fp256.py -- do not edit by hand; edit the generator.
+HEADER = """// GENERATED by gen_fp256.py -- do not edit by hand; edit the generator.
 //
-// P-256 Montgomery multiplication core for sm_100a: r = a*b*2^-256 mod p,
-// canonical in [0,p) (for ANY 256-bit a,b: the exact quotient t=(ab+mp)/2^256
-// with one conditional subtraction, which is what the reference's
-// mgry_mul computes: include/ecsimd/mgry_ops.h:31-35, mul.h:150-158,
-// mgry_mul.h:84-121).
+// P-256 Montgomery multiplication / squaring cores for sm_100a.  Both return the exact
+// nine-word quotient t = (T + m*p) / 2^256 with m = -T/p mod 2^256 (t < 2^256 + p), for T = a*b
+// resp. T = a*a and ANY 256-bit operands; the caller (fp256.cuh) subtracts p once if t >= p,
+// which is what the reference's mgry_mul / mgry_reduce compute
+// (include/ecsimd/mgry_ops.h:31-35, mul.h:150-158, mgry_mul.h:84-121).
 //
-// Schedule: CIOS on 32-bit limbs with two pair-aligned accumulators (E: even
-// word positions, O: odd) so that every 32x32+64 multiply-add is a single
-// IMAD.WIDE.U32(.X) with the carry in a predicate; the reduction by
-// p+1 = {1@3, 1@6, 0xffffffff@7} needs three multiply-adds per row and no
-// multiplication by m' (m' = 1).  See gen_fp256.py for the derivation and the
-// offline carry-bound simulation.
+// Design (see gen_fp256.py for the schedules and the offline carry-bound simulation):
+//  * 32-bit limbs; every 32x32+64 product is ONE IMAD.WIDE.U32(.X) (ptxas fuses
+//    mad.lo.cc/madc.hi.cc on an aligned register pair, carry in a predicate).  To keep every
+//    product pair-aligned there are two accumulators: E (pairs at even word positions) takes
+//    a_i*b_j with i+j even, O the others.  Products are strung into chains of ascending pairs
+//    that end only where no carry can exist, so the multiplier costs exactly 64 (squaring: 36)
+//    IMAD.WIDE and 6 (0) captured carries.
+//  * p = 2^256 - 2^224 + 2^192 + 2^96 - 1 gives -1/p = 1 mod 2^32 and m*p = (m<<256) - (m<<224)
+//    + (m<<192) + (m<<96) - m: the reduction is four shifted multi-word add/sub chains on the
+//    ALU pipe and needs no multiplication at all.
 #pragma once
 #include <cstdint>
 
 namespace ecb200 {
 
-'''
+"""
+
+
+def _emit_fn(name, g, nin):
+    regs = set()
+    for s in g.stmts:
+        regs.update(s["rw"]); regs.update(s["wo"]); regs.update(s["ro"])
+    params = ["h%d" % k for k in range(9)] + ["a%d" % k for k in range(8)] + (["b%d" % k for k in range(8)] if nin == 2 else [])
+    local = sorted(regs - set(params), key=lambda x: (x.rstrip("0123456789"), int("0" + "".join(ch for ch in x if ch.isdigit()))))
+    txt = "__device__ __forceinline__ void %s(\n" % name
+    txt += "    " + ", ".join("uint32_t& h%d" % k for k in range(9)) + ",\n"
+    txt += "    " + ", ".join("uint32_t a%d" % k for k in range(8))
+    if nin == 2:
+        txt += ",\n    " + ", ".join("uint32_t b%d" % k for k in range(8))
+    txt += ") {\n"
+    txt += "  uint32_t " + ", ".join(local) + ";\n"
+    txt += g.cxx() + "\n}\n\n"
+    return txt
 
 
 def emit_header(path):
-    g, touched = gen_mul()
-    n = check(g)
-    regs = sorted(touched, key=lambda s: (s[0], int(s[1:])))
-    txt = HEADER
-    txt += "__device__ __forceinline__ void fp_mul_words(\n"
-    txt += "    uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t& r4, uint32_t& r5, uint32_t& r6, uint32_t& r7,\n"
-    txt += "    uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7,\n"
-    txt += "    uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4, uint32_t b5, uint32_t b6, uint32_t b7) {\n"
-    txt += "  uint32_t " + ", ".join(regs) + ";\n"
-    txt += "  uint32_t " + ", ".join("t%d" % k for k in range(9)) + ";\n"
-    txt += "  uint32_t " + ", ".join("d%d" % k for k in range(8)) + ", mk, m1;\n"
-    txt += g.cxx() + "\n}\n\n}  // namespace ecb200\n"
+    gm, gs = gen_mul(), gen_sqr()
+    nm = check(gm, unary=False)
+    ns = check(gs, unary=True)
+    txt = HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1) + "}  // namespace ecb200\n"
     with open(path, "w") as f:
         f.write(txt)
-    return n, g
+    return nm + ns, gm, gs
+
+
+def _stats(g):
+    wide = sum(1 for i in g.ir if i[0] in ("mulw", "madw"))
+    other = sum(1 for i in g.ir if i[0] not in ("mulw", "madw", "endchain"))
+    pairs = sum(1 for i in g.ir if i[0] == "addw")
+    return wide, other + pairs
 
 
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
     if "--check-only" in sys.argv:
-        g, _ = gen_mul()
-        print("simulated cases ok:", check(g, 20000))
+        print("mul: simulated cases ok:", check(gen_mul(), False, 20000))
+        print("sqr: simulated cases ok:", check(gen_sqr(), True, 20000))
     else:
-        n, g = emit_header(os.path.join(here, "fp256_mul_gen.cuh"))
-        nimad = sum(1 for i in g.ir if i[0] in ("mulw", "madw"))
-        print("wrote fp256_mul_gen.cuh; simulated %d cases ok; wide multiply-adds: %d" % (n, nimad))
+        n, gm, gs = emit_header(os.path.join(here, "fp256_mul_gen.cuh"))
+        print("wrote fp256_mul_gen.cuh; simulated %d cases ok; mul: %d wide multiply-adds + %d ALU ops; sqr: %d + %d"
+              % ((n,) + _stats(gm) + _stats(gs)))
