@@ -78,15 +78,26 @@ static __device__ __noinline__ uint32_t fp_ge_p_rare(uint32_t t0, uint32_t t1, u
   return (t0 & t1 & t2) == 0xffffffffu;
 }
 
+// Two ways of treating the (astronomically) rare cases of the fast paths below:
+//   Exact : resolve them in place with a branch (streaming field / point kernels).
+//   Lazy  : only record that one may have happened; the caller re-runs the whole computation
+//           in Exact mode if anything was recorded (the scalar-mult ladder: keeps branches and
+//           calls out of its hot loop).  `top` collects the largest pre-reduction top word seen
+//           (0xffffffff <=> the conditional subtraction may have been decided wrongly);
+//           `dirty` is set when a squaring operand is in the reference's lost-carry set.
+struct Exact {};
+struct Lazy {
+  uint32_t top = 0;
+  uint32_t dirty = 0;
+  __device__ __forceinline__ bool flagged() const { return top == 0xffffffffu || dirty != 0u; }
+};
+
 // The single conditional subtraction every modular op ends with (sub_if_above, sub.h:46-69):
 // given the 257-bit value (c:s), return it minus p if it is >= p.  c == 1 always subtracts;
 // c == 0 subtracts only if s >= p, which needs s7 == 0xffffffff (probability 2^-32 on uniform
 // data): that case branches to an exact comparison, everything else is one 8-word add of
 // (2^256 - p) & mask = {sub, 0, 0, mask, mask, mask, mask<<1, 0}.
-__device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c) {
-  uint32_t sub = c;
-  if (__builtin_expect(s.v[7] == 0xffffffffu && c == 0u, 0))
-    sub = fp_ge_p_rare(s.v[0], s.v[1], s.v[2], s.v[3], s.v[4], s.v[5], s.v[6]);
+__device__ __forceinline__ fe fp_add_k(const fe& s, uint32_t sub) {
   const uint32_t mask = 0u - sub, k6 = mask + mask;
   fe r;
   asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, 0; addc.cc.u32 %2, %10, 0; addc.cc.u32 %3, %11, %17; "
@@ -96,8 +107,20 @@ __device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c) {
         "r"(sub), "r"(mask), "r"(k6));
   return r;
 }
+__device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c, Exact&) {
+  uint32_t sub = c;
+  if (__builtin_expect(s.v[7] == 0xffffffffu && c == 0u, 0))
+    sub = fp_ge_p_rare(s.v[0], s.v[1], s.v[2], s.v[3], s.v[4], s.v[5], s.v[6]);
+  return fp_add_k(s, sub);
+}
+__device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c, Lazy& z) {
+  z.top = max(z.top, s.v[7]);
+  return fp_add_k(s, c);
+}
+__device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c) { Exact e; return fp_reduce_once(s, c, e); }
 
-__device__ __forceinline__ fe fp_add(const fe& a, const fe& b) {
+template <class M>
+__device__ __forceinline__ fe fp_add(const fe& a, const fe& b, M& mode) {
   fe s;
   uint32_t c;
   asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20; "
@@ -106,33 +129,40 @@ __device__ __forceinline__ fe fp_add(const fe& a, const fe& b) {
       : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7]), "=r"(c)
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
         "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-  return fp_reduce_once(s, c);
+  return fp_reduce_once(s, c, mode);
 }
+__device__ __forceinline__ fe fp_add(const fe& a, const fe& b) { Exact e; return fp_add(a, b, e); }
 
-__device__ __forceinline__ fe fp_shl1(const fe& a) {
+template <class M>
+__device__ __forceinline__ fe fp_shl1(const fe& a, M& mode) {
   fe s;
   const uint32_t c = a.v[7] >> 31;
 #pragma unroll
   for (int i = 7; i > 0; i--) s.v[i] = __funnelshift_l(a.v[i - 1], a.v[i], 1);
   s.v[0] = a.v[0] << 1;
-  return fp_reduce_once(s, c);
+  return fp_reduce_once(s, c, mode);
 }
-template <int COUNT>
-__device__ __forceinline__ fe fp_shl(const fe& a) {
+__device__ __forceinline__ fe fp_shl1(const fe& a) { Exact e; return fp_shl1(a, e); }
+template <int COUNT, class M>
+__device__ __forceinline__ fe fp_shl(const fe& a, M& mode) {
   fe r = a;
 #pragma unroll
-  for (int i = 0; i < COUNT; i++) r = fp_shl1(r);
+  for (int i = 0; i < COUNT; i++) r = fp_shl1(r, mode);
   return r;
 }
+template <int COUNT>
+__device__ __forceinline__ fe fp_shl(const fe& a) { Exact e; return fp_shl<COUNT>(a, e); }
 
-__device__ __forceinline__ fe fp_mul(const fe& a, const fe& b) {
+template <class M>
+__device__ __forceinline__ fe fp_mul(const fe& a, const fe& b, M& mode) {
   fe t;
   uint32_t t8;
   fp_mul_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8,
             a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
             b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6], b.v[7]);
-  return fp_reduce_once(t, t8);
+  return fp_reduce_once(t, t8, mode);
 }
+__device__ __forceinline__ fe fp_mul(const fe& a, const fe& b) { Exact e; return fp_mul(a, b, e); }
 
 // ---- squaring ------------------------------------------------------------------------
 // The reference's square() (mul.h:160-212) accumulates the doubled cross products
@@ -226,13 +256,18 @@ __device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a) {
   return m;
 }
 
-template <bool QUIRK = true>
-__device__ __forceinline__ fe fp_sqr(const fe& a) {
+template <bool QUIRK, class M>
+__device__ __forceinline__ fe fp_sqr_core(const fe& a, M& mode) {
   fe t;
   uint32_t t8;
   fp_sqr_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8,
             a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7]);
-  fe r = fp_reduce_once(t, t8);
+  return fp_reduce_once(t, t8, mode);
+}
+
+template <bool QUIRK>
+__device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
+  fe r = fp_sqr_core<QUIRK>(a, mode);
   if (QUIRK) {
     if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
       uint32_t in[8], out[8];
@@ -247,6 +282,21 @@ __device__ __forceinline__ fe fp_sqr(const fe& a) {
   }
   return r;
 }
+template <bool QUIRK>
+__device__ __forceinline__ fe fp_sqr(const fe& a, Lazy& mode) {
+  const fe r = fp_sqr_core<QUIRK>(a, mode);
+  if (QUIRK) {
+    if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
+      uint32_t in[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) in[i] = a.v[i];
+      if (fp_sqr_quirk_filter_exact(in)) mode.dirty = 1u;
+    }
+  }
+  return r;
+}
+template <bool QUIRK = true>
+__device__ __forceinline__ fe fp_sqr(const fe& a) { Exact e; return fp_sqr<QUIRK>(a, e); }
 
 // gfp.h:60-64: opposite(a) = (p-1)R - (a - R)
 __device__ __forceinline__ fe fp_neg(const fe& a) { return fp_sub(fe_PM1R(), fp_sub(a, fe_R())); }

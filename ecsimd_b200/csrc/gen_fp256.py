@@ -331,8 +331,12 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops):
                 lo, hi = R(acc, w), R(acc, w + 1)
                 last = n == len(ch) - 1
                 fresh = (lo not in touched, hi not in touched)
-                if allfresh:
+                if allfresh and not (n == 0 and w == 0):
                     g.mulw(lo, hi, xa % i, xb % j)
+                elif allfresh:
+                    # word 0 of the product is m_0, read four more times by the reduction: written as a
+                    # carry-setting multiply-add so that ptxas keeps it instead of recomputing it
+                    g.madw(lo, hi, xa % i, xb % j, False, True, fresh=(True, True))
                 else:
                     # the carry out of the last step is dropped only where it cannot exist
                     safe_end = last and (all(fresh) or w == top)
@@ -448,12 +452,11 @@ def gen_sqr():
     g.end()
     # T = d + sum a_i^2 2^(64 i): one chain of eight multiply-adds on the pairs (2i, 2i+1)
     g.begin()
-    g.mulw("t0", "t1x", "a0", "a0")
-    g.add32("t1", "t1x", "d1", False, True)
+    g.madw("t0", "d1", "a0", "a0", False, True, fresh=(True, False))
     for i in range(1, 8):
         g.madw("d%d" % (2 * i), "d%d" % (2 * i + 1), "a%d" % i, "a%d" % i, True, i < 7)
     g.end()
-    T = ["t0", "t1"] + ["d%d" % w for w in range(2, 16)]
+    T = ["t0"] + ["d%d" % w for w in range(1, 16)]
     emit_reduction(g, T)
     return g
 

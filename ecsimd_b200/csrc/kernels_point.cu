@@ -40,27 +40,28 @@ __global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   jac a = load_jac(A, n, i);
+  Exact md;
   if (OP == PO_DBLU) {
-    const jac r = pt_dblu<QUIRK>(a);
+    const jac r = pt_dblu<QUIRK>(a, md);
     store_jac(out1, n, i, a);
     store_jac(out2, n, i, r);
   } else if (OP == PO_TRPLU) {
-    const jac r = pt_trplu<QUIRK>(a);
+    const jac r = pt_trplu<QUIRK>(a, md);
     store_jac(out1, n, i, a);
     store_jac(out2, n, i, r);
   } else if (OP == PO_ZADDU) {
     const jac b = load_jac(B, n, i);
-    const jac r = pt_zaddu<QUIRK>(a, b);
+    const jac r = pt_zaddu<QUIRK>(a, b, md);
     store_jac(out1, n, i, a);
     store_jac(out2, n, i, r);
   } else if (OP == PO_ZDAU) {
     jac q = load_jac(B, n, i);
-    const jac r = pt_zdau<QUIRK>(a, q);
+    const jac r = pt_zdau<QUIRK>(a, q, md);
     store_jac(out1, n, i, q);
     store_jac(out2, n, i, r);
   } else if (OP == PO_ADDZ21) {
     const fe bx = S::load(B, n, i, 3, 0), by = S::load(B, n, i, 3, 1);
-    store_jac(out1, n, i, pt_add_z2_1<QUIRK>(a, bx, by));
+    store_jac(out1, n, i, pt_add_z2_1<QUIRK>(a, bx, by, md));
   }
 }
 
@@ -247,7 +248,7 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   if ((rc = st.out(out, 3, &dout))) return rc;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   const bool q = quirk_on(flags);
-  static const int minb = [] { const char* e = getenv("ECB200_SM_MINB"); return e ? atoi(e) : 3; }();
+  static const int minb = [] { const char* e = getenv("ECB200_SM_MINB"); return e ? atoi(e) : 512; }();  // development knob
   if (mode == 0 && minb >= 384) {
     const unsigned b2 = (unsigned)((n + minb - 1) / minb);
     if (minb == 384) {

@@ -24,18 +24,18 @@ struct jac {
 
 // DBLU: returns 2P; rewrites P as the same point with Z(P) = Z(2P).  Input Z is ignored
 // (the reference requires Z == R and never reads it).
-template <bool QUIRK>
-__device__ __forceinline__ jac pt_dblu(jac& P) {
-  const fe B = fp_sqr<QUIRK>(P.x);
-  const fe E = fp_sqr<QUIRK>(P.y);
-  const fe L = fp_sqr<QUIRK>(E);
-  const fe S = fp_shl1(fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(P.x, E)), B), L));
-  const fe M = fp_add(fp_add(fp_shl1(B), B), fe_AM());
+template <bool QUIRK, class MD>
+__device__ __forceinline__ jac pt_dblu(jac& P, MD& md) {
+  const fe B = fp_sqr<QUIRK>(P.x, md);
+  const fe E = fp_sqr<QUIRK>(P.y, md);
+  const fe L = fp_sqr<QUIRK>(E, md);
+  const fe S = fp_shl1(fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(P.x, E, md), md), B), L), md);
+  const fe M = fp_add(fp_add(fp_shl1(B, md), B, md), fe_AM(), md);
   jac r;
-  r.x = fp_sub(fp_sqr<QUIRK>(M), fp_shl1(S));
-  const fe L8 = fp_shl<3>(L);
-  r.y = fp_sub(fp_mul(M, fp_sub(S, r.x)), L8);
-  r.z = fp_shl1(P.y);
+  r.x = fp_sub(fp_sqr<QUIRK>(M, md), fp_shl1(S, md));
+  const fe L8 = fp_shl<3>(L, md);
+  r.y = fp_sub(fp_mul(M, fp_sub(S, r.x), md), L8);
+  r.z = fp_shl1(P.y, md);
   P.x = S;
   P.y = L8;
   P.z = r.z;
@@ -43,19 +43,19 @@ __device__ __forceinline__ jac pt_dblu(jac& P) {
 }
 
 // ZADDU: returns P + O (same Z required); rewrites P with the Z of the result.
-template <bool QUIRK>
-__device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O) {
+template <bool QUIRK, class MD>
+__device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O, MD& md) {
   const fe dx = fp_sub(P.x, O.x);
   const fe dy = fp_sub(P.y, O.y);
-  const fe C = fp_sqr<QUIRK>(dx);
-  const fe W1 = fp_mul(P.x, C);
-  const fe W2 = fp_mul(O.x, C);
-  const fe D = fp_sqr<QUIRK>(dy);
-  const fe A1 = fp_mul(P.y, fp_sub(W1, W2));
+  const fe C = fp_sqr<QUIRK>(dx, md);
+  const fe W1 = fp_mul(P.x, C, md);
+  const fe W2 = fp_mul(O.x, C, md);
+  const fe D = fp_sqr<QUIRK>(dy, md);
+  const fe A1 = fp_mul(P.y, fp_sub(W1, W2), md);
   jac r;
   r.x = fp_sub(fp_sub(D, W1), W2);
-  r.y = fp_sub(fp_mul(dy, fp_sub(W1, r.x)), A1);
-  r.z = fp_mul(P.z, dx);
+  r.y = fp_sub(fp_mul(dy, fp_sub(W1, r.x), md), A1);
+  r.z = fp_mul(P.z, dx, md);
   P.x = W1;
   P.y = A1;
   P.z = r.z;
@@ -64,71 +64,74 @@ __device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O) {
 
 // ZDAU core on bare coordinates: (X1,Y1) <- 2*(X1,Y1) + (X2,Y2); (X2,Y2) <- the same
 // point (X2,Y2) re-scaled to the new common Z; Z <- new Z.
-template <bool QUIRK>
-__device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z) {
+template <bool QUIRK, class MD>
+__device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z, MD& md) {
   const fe dx = fp_sub(X1, X2);
   const fe dy = fp_sub(Y1, Y2);
-  const fe Cp = fp_sqr<QUIRK>(dx);
-  const fe W1p = fp_mul(X1, Cp);
-  const fe W2p = fp_mul(X2, Cp);
-  const fe Dp = fp_sqr<QUIRK>(dy);
-  const fe A1p = fp_mul(Y1, fp_sub(W1p, W2p));
+  const fe Cp = fp_sqr<QUIRK>(dx, md);
+  const fe W1p = fp_mul(X1, Cp, md);
+  const fe W2p = fp_mul(X2, Cp, md);
+  const fe Dp = fp_sqr<QUIRK>(dy, md);
+  const fe A1p = fp_mul(Y1, fp_sub(W1p, W2p), md);
   const fe X3pc = fp_sub(fp_sub(Dp, W1p), W2p);
   const fe e3 = fp_sub(X3pc, W1p);
-  const fe C = fp_sqr<QUIRK>(e3);
-  const fe A2 = fp_shl1(A1p);
-  // Y3p = ((Y1-Y2) + (W1p-X3pc))^2 - Dp - C - 2*A1p
-  const fe Y3p = fp_sub(fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(dy, fp_sub(W1p, X3pc))), Dp), C), A2);
-  const fe W1 = fp_mul(fp_shl<2>(X3pc), C);
-  const fe W2 = fp_mul(fp_shl<2>(W1p), C);
+  const fe C = fp_sqr<QUIRK>(e3, md);
+  const fe A2 = fp_shl1(A1p, md);
+  // Y3p = ((Y1-Y2) + (W1p-X3pc))^2 - Dp - C - 2*A1p        [(W1p - X3pc) = -e3]
+  const fe Y3p = fp_sub(fp_sub(fp_sub(fp_sqr<QUIRK>(fp_sub(dy, e3), md), Dp), C), A2);
+  // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once instead of each multiplicand
+  const fe C4 = fp_shl<2>(C, md);
+  const fe W1 = fp_mul(X3pc, C4, md);
+  const fe W2 = fp_mul(W1p, C4, md);
+  const fe W12 = fp_add(W1, W2, md);
   const fe ym = fp_sub(Y3p, A2);
-  const fe yp = fp_add(Y3p, A2);
-  const fe D = fp_sqr<QUIRK>(ym);
-  const fe A1 = fp_mul(Y3p, fp_sub(W1, W2));
-  const fe X3 = fp_sub(fp_sub(D, W1), W2);
-  const fe Y3 = fp_sub(fp_mul(ym, fp_sub(W1, X3)), A1);
-  // Z3 = Z * ((X1 - X2 + X3pc - W1p)^2 - Cp - C)
-  const fe Z3 = fp_mul(Z, fp_sub(fp_sub(fp_sqr<QUIRK>(fp_sub(fp_add(dx, X3pc), W1p)), Cp), C));
-  const fe Dc = fp_sqr<QUIRK>(yp);
-  const fe X2n = fp_sub(fp_sub(Dc, W1), W2);
-  const fe Y2n = fp_sub(fp_mul(yp, fp_sub(W1, X2n)), A1);
+  const fe yp = fp_add(Y3p, A2, md);
+  const fe D = fp_sqr<QUIRK>(ym, md);
+  const fe A1 = fp_mul(Y3p, fp_sub(W1, W2), md);
+  const fe X3 = fp_sub(D, W12);
+  const fe Y3 = fp_sub(fp_mul(ym, fp_sub(W1, X3), md), A1);
+  // Z3 = Z * ((X1 - X2 + X3pc - W1p)^2 - Cp - C)           [X3pc - W1p = e3]
+  const fe Z3 = fp_mul(Z, fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(dx, e3, md), md), Cp), C), md);
+  const fe Dc = fp_sqr<QUIRK>(yp, md);
+  const fe X2n = fp_sub(Dc, W12);
+  const fe Y2n = fp_sub(fp_mul(yp, fp_sub(W1, X2n), md), A1);
   X1 = X3; Y1 = Y3;
   X2 = X2n; Y2 = Y2n;
   Z = Z3;
 }
 
 // ZDAU(P, Q&): returns 2P + Q, rewrites Q (same point, new Z).  Z of P is used.
-template <bool QUIRK>
-__device__ __forceinline__ jac pt_zdau(const jac& P, jac& Q) {
+template <bool QUIRK, class MD>
+__device__ __forceinline__ jac pt_zdau(const jac& P, jac& Q, MD& md) {
   jac r = P;
-  pt_zdau_xy<QUIRK>(r.x, r.y, Q.x, Q.y, r.z);
+  pt_zdau_xy<QUIRK>(r.x, r.y, Q.x, Q.y, r.z, md);
   Q.z = r.z;
   return r;
 }
 
 // ADD_Z2_1(A, B): A + B with Z(B) == R assumed (B.z is never read).
-template <bool QUIRK>
-__device__ __forceinline__ jac pt_add_z2_1(const jac& A, const fe& X2, const fe& Y2) {
-  const fe Z1Z1 = fp_sqr<QUIRK>(A.z);
-  const fe U2 = fp_mul(X2, Z1Z1);
-  const fe S2 = fp_mul(fp_mul(Y2, A.z), Z1Z1);
+template <bool QUIRK, class MD>
+__device__ __forceinline__ jac pt_add_z2_1(const jac& A, const fe& X2, const fe& Y2, MD& md) {
+  const fe Z1Z1 = fp_sqr<QUIRK>(A.z, md);
+  const fe U2 = fp_mul(X2, Z1Z1, md);
+  const fe S2 = fp_mul(fp_mul(Y2, A.z, md), Z1Z1, md);
   const fe H = fp_sub(U2, A.x);
-  const fe HH = fp_sqr<QUIRK>(H);
-  const fe I = fp_shl<2>(HH);
-  const fe J = fp_mul(H, I);
-  const fe r = fp_shl1(fp_sub(S2, A.y));
-  const fe V = fp_mul(A.x, I);
+  const fe HH = fp_sqr<QUIRK>(H, md);
+  const fe I = fp_shl<2>(HH, md);
+  const fe J = fp_mul(H, I, md);
+  const fe r = fp_shl1(fp_sub(S2, A.y), md);
+  const fe V = fp_mul(A.x, I, md);
   jac o;
-  o.x = fp_sub(fp_sub(fp_sqr<QUIRK>(r), J), fp_shl1(V));
-  o.y = fp_sub(fp_mul(r, fp_sub(V, o.x)), fp_mul(fp_shl1(A.y), J));
-  o.z = fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(A.z, H)), Z1Z1), HH);
+  o.x = fp_sub(fp_sub(fp_sqr<QUIRK>(r, md), J), fp_shl1(V, md));
+  o.y = fp_sub(fp_mul(r, fp_sub(V, o.x), md), fp_mul(fp_shl1(A.y, md), J, md));
+  o.z = fp_sub(fp_sub(fp_sqr<QUIRK>(fp_add(A.z, H, md), md), Z1Z1), HH);
   return o;
 }
 
-template <bool QUIRK>
-__device__ __forceinline__ jac pt_trplu(jac& P) {
-  const jac dbl = pt_dblu<QUIRK>(P);
-  return pt_zaddu<QUIRK>(P, dbl);
+template <bool QUIRK, class MD>
+__device__ __forceinline__ jac pt_trplu(jac& P, MD& md) {
+  const jac dbl = pt_dblu<QUIRK>(P, md);
+  return pt_zaddu<QUIRK>(P, dbl, md);
 }
 
 // scalar_mult: Joye's right-to-left co-Z double-add ladder with bit 0 forced to 1 and
@@ -138,29 +141,32 @@ __device__ __forceinline__ jac pt_trplu(jac& P) {
 // opening swap of step b+1 are merged into one swap on (bit_b xor bit_{b+1}).
 // SYNC: all warps of the block meet at a barrier once per ladder step, so that they walk
 // the (large, fully unrolled) loop body together and share instruction-cache lines.
-template <bool QUIRK, bool SYNC = false>
-__device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& Px, const fe& Py) {
+template <bool QUIRK, bool SYNC, class MD>
+__device__ __forceinline__ jac pt_scalar_mult_mode(const uint32_t (&k)[8], const fe& Px, const fe& Py, MD& md) {
   jac P;
   P.x = Px; P.y = Py; P.z = fe_R();
   const fe oppY = fp_neg(Py);
-  jac base = pt_trplu<QUIRK>(P);
+  jac base = pt_trplu<QUIRK>(P, md);
   fe Z = base.z;
   // state: (base.x, base.y) and (P.x, P.y) share Z.
   uint32_t prev = (k[0] >> 1) & 1u;  // pending swap
+  uint32_t w = k[0] >> 2;
 #pragma unroll 1
   for (int b = 2; b < 256; b++) {
-    const uint32_t bit = (k[b >> 5] >> (b & 31)) & 1u;
+    if ((b & 31) == 0) w = k[b >> 5];
+    const uint32_t bit = w & 1u;
+    w >>= 1;
     const uint32_t sw = prev ^ bit;
     fe_cswap(sw, P.x, base.x);
     fe_cswap(sw, P.y, base.y);
-    pt_zdau_xy<QUIRK>(base.x, base.y, P.x, P.y, Z);
+    pt_zdau_xy<QUIRK>(base.x, base.y, P.x, P.y, Z, md);
     prev = bit;
     if (SYNC) __syncthreads();
   }
   fe_cswap(prev, P.x, base.x);
   fe_cswap(prev, P.y, base.y);
   P.z = Z;
-  const jac Psub = pt_add_z2_1<QUIRK>(P, Px, oppY);
+  const jac Psub = pt_add_z2_1<QUIRK>(P, Px, oppY, md);
   const bool odd = (k[0] & 1u) != 0u;
   jac out;
 #pragma unroll
@@ -170,6 +176,31 @@ __device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& 
     out.z.v[i] = odd ? P.z.v[i] : Psub.z.v[i];
   }
   return out;
+}
+
+// The exact re-run for lanes the fast ladder flagged (a handful per million): same ladder, every
+// rare case resolved in place.  Kept out of line so that it costs the hot path nothing.
+template <bool QUIRK>
+__device__ __noinline__ void pt_scalar_mult_exact(uint32_t* out24, const uint32_t* k8, const uint32_t* xy16) {
+  uint32_t k[8];
+  fe px, py;
+  for (int i = 0; i < 8; i++) { k[i] = k8[i]; px.v[i] = xy16[i]; py.v[i] = xy16[8 + i]; }
+  Exact md;
+  const jac r = pt_scalar_mult_mode<QUIRK, false>(k, px, py, md);
+  for (int i = 0; i < 8; i++) { out24[i] = r.x.v[i]; out24[8 + i] = r.y.v[i]; out24[16 + i] = r.z.v[i]; }
+}
+
+template <bool QUIRK, bool SYNC = false>
+__device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& Px, const fe& Py) {
+  Lazy md;
+  jac r = pt_scalar_mult_mode<QUIRK, SYNC>(k, Px, Py, md);
+  if (__builtin_expect(md.flagged(), 0)) {
+    uint32_t kk[8], xy[16], o[24];
+    for (int i = 0; i < 8; i++) { kk[i] = k[i]; xy[i] = Px.v[i]; xy[8 + i] = Py.v[i]; }
+    pt_scalar_mult_exact<QUIRK>(o, kk, xy);
+    for (int i = 0; i < 8; i++) { r.x.v[i] = o[i]; r.y.v[i] = o[8 + i]; r.z.v[i] = o[16 + i]; }
+  }
+  return r;
 }
 
 }  // namespace ecb200

@@ -17,8 +17,11 @@ __device__ __noinline__ fe sqr_call(fe a) { return fp_sqr<true>(a); }
 
 template <bool CALLS>
 __device__ __forceinline__ fe MUL(const fe& a, const fe& b) { return CALLS ? mul_call(a, b) : fp_mul(a, b); }
+#ifndef BENCH_QUIRK
+#define BENCH_QUIRK true
+#endif
 template <bool CALLS>
-__device__ __forceinline__ fe SQR(const fe& a) { return CALLS ? sqr_call(a) : fp_sqr<true>(a); }
+__device__ __forceinline__ fe SQR(const fe& a) { return CALLS ? sqr_call(a) : fp_sqr<BENCH_QUIRK>(a); }
 
 template <bool CALLS>
 __device__ __forceinline__ void zdau_v(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z) {
@@ -53,6 +56,7 @@ template <bool CALLS, bool SYNC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_zdau(uint32_t* io, int iters) {
   const size_t t = (size_t)threadIdx.x + (size_t)blockIdx.x * blockDim.x;
   fe v[5];
+  Lazy md;
   for (int c = 0; c < 5; c++)
     for (int i = 0; i < 8; i++) v[c].v[i] = io[t * 40 + c * 8 + i];
 #pragma unroll 1
@@ -60,9 +64,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_zdau(uint32_t* io, int iters)
     const uint32_t sw = (v[0].v[0] >> (it & 31)) & 1u;  // data-dependent swap like the ladder
     fe_cswap(sw, v[0], v[2]);
     fe_cswap(sw, v[1], v[3]);
-    zdau_v<CALLS>(v[0], v[1], v[2], v[3], v[4]);
+    if (CALLS) zdau_v<CALLS>(v[0], v[1], v[2], v[3], v[4]);
+    else pt_zdau_xy<BENCH_QUIRK>(v[0], v[1], v[2], v[3], v[4], md);
     if (SYNC) __syncthreads();
   }
+  if (md.flagged()) v[0].v[0] ^= 1;  // keep the flags alive
   for (int c = 0; c < 5; c++)
     for (int i = 0; i < 8; i++) io[t * 40 + c * 8 + i] = v[c].v[i];
 }
@@ -101,6 +107,8 @@ int main(int argc, char** argv) {
   cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
   run("inline_128x3", k_zdau<false, false, 128, 3>, 128, 3, d, iters);
   run("inline_sync_384x1", k_zdau<false, true, 384, 1>, 384, 1, d, iters);
+  run("inline_sync_512x1", k_zdau<false, true, 512, 1>, 512, 1, d, iters);
+
 #if VARIANT_CALLS
   run("calls_128x3", k_zdau<true, false, 128, 3>, 128, 3, d, iters);
   run("calls_sync_384x1", k_zdau<true, true, 384, 1>, 384, 1, d, iters);
