@@ -1,0 +1,240 @@
+// ecsimd.hpp -- drop-in C++ surface of aguinet/ecsimd's P-256 hot path over the B200 engine.
+//
+// Same names, argument meaning and (absence of) error behaviour as the reference headers,
+// re-implemented as thin POD wrappers around the C ABI of include/ecb200.h (the reference's
+// EVE-based templates cannot be compiled by nvcc and are not needed):
+//
+//   ecsimd::bignum_256, wide_bignum<bignum_256>        include/ecsimd/bignum.h:38-102
+//   ecsimd::wide_mgry_bignum, mgry_add/sub/mul/sqr/..   include/ecsimd/mgry.h:28-66, mgry_ops.h:10-101
+//   ecsimd::GFp (+ operator+,-,*, gfp_shift_left, sqr,  include/ecsimd/gfp.h:17-115
+//               inverse, opposite)
+//   ecsimd::wide_curve_point, wide_jacobian_curve_point include/ecsimd/curve_point.h:13-43,
+//                                                       jacobian_curve_point.h:12-68
+//   ecsimd::curve_group<curve_nist_p256>::{DBLU, ZADDU, ZDAU, ADD_Z2_1, TRPLU, scalar_mult,
+//               scalar_mult_1s, WG, WJG}                include/ecsimd/curve_group.h:21-252
+//   scalar_mult_p256(WBN const&, WJCP const&)           lib/scalar_mult_p256.cpp:12-14
+//
+// Object layout is the reference's: a wide_bignum is 128 bytes, 32-byte aligned, u64 word index
+// limb*4 + lane; a wide_jacobian_curve_point is x|y|z = 384 bytes.  Arrays of these objects can
+// therefore be handed to the batch overloads (and to the C ABI with ECB200_LAYOUT_PACK4) as is.
+//
+// The 4-lane calls exist for source compatibility; throughput comes from the batch overloads
+// (`std::size_t npacks` packs per call), which is how a B200 wants to be fed.
+#pragma once
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../ecb200.h"
+
+namespace ecsimd {
+
+namespace detail {
+inline void check(int rc) {
+  // the reference has no error channel at all; a failing CUDA call is the one thing we cannot
+  // express as "deterministic garbage", so it throws
+  if (rc != ECB200_OK) throw std::runtime_error(std::string("ecb200: ") + ecb200_last_error());
+}
+constexpr uint32_t kHostPack = ECB200_LAYOUT_PACK4 | ECB200_MEM_HOST;
+}  // namespace detail
+
+// ---- bignum.h ------------------------------------------------------------------------------
+struct bignum_256 {
+  using limb_type = uint64_t;
+  static constexpr std::size_t nlimbs = 4;
+  uint64_t limb[4];  // least-significant first
+  static bignum_256 from(uint64_t v0) { return bignum_256{{v0, 0, 0, 0}}; }
+  friend bool operator==(bignum_256 const& a, bignum_256 const& b) { return std::memcmp(&a, &b, sizeof a) == 0; }
+};
+
+// serialization.h:12-48 (big-endian 32-byte strings) and literals.h:28-43
+inline bignum_256 bn_from_bytes_BE(const uint8_t* b) {
+  bignum_256 r{};
+  for (int i = 0; i < 32; i++) r.limb[(31 - i) / 8] |= uint64_t(b[i]) << (8 * ((31 - i) % 8));
+  return r;
+}
+inline void bn_to_bytes_BE(uint8_t* out, bignum_256 const& v) {
+  for (int i = 0; i < 32; i++) out[i] = uint8_t(v.limb[(31 - i) / 8] >> (8 * ((31 - i) % 8)));
+}
+inline bignum_256 bn_from_hex(const char* hex64) {
+  uint8_t b[32];
+  auto nib = [](char c) -> int { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; };
+  for (int i = 0; i < 32; i++) b[i] = uint8_t(nib(hex64[2 * i]) << 4 | nib(hex64[2 * i + 1]));
+  return bn_from_bytes_BE(b);
+}
+
+template <class BN>
+struct wide_bignum;
+template <>
+struct alignas(32) wide_bignum<bignum_256> {
+  using value_type = bignum_256;
+  static constexpr std::size_t cardinal = 4;
+  uint64_t w[16];  // word index = limb*4 + lane
+  wide_bignum() = default;
+  explicit wide_bignum(bignum_256 const& v) { for (int l = 0; l < 4; l++) for (int k = 0; k < 4; k++) w[l * 4 + k] = v.limb[l]; }
+  template <class F, class = decltype(std::declval<F>()(0, 4))>
+  explicit wide_bignum(F&& gen) { for (int k = 0; k < 4; k++) set(k, gen(k, 4)); }
+  bignum_256 get(int lane) const { return bignum_256{{w[lane], w[4 + lane], w[8 + lane], w[12 + lane]}}; }
+  void set(int lane, bignum_256 const& v) { for (int l = 0; l < 4; l++) w[l * 4 + lane] = v.limb[l]; }
+  friend bool operator==(wide_bignum const& a, wide_bignum const& b) { return std::memcmp(a.w, b.w, sizeof a.w) == 0; }
+};
+using WBN256 = wide_bignum<bignum_256>;
+static_assert(sizeof(WBN256) == 128 && alignof(WBN256) == 32, "must match eve::wide<bignum_256, fixed<4>>");
+
+struct curve_nist_p256 {  // curve_nist_p256.h:14-32
+  using bn_type = bignum_256;
+  static bignum_256 P() { return bn_from_hex("ffffffff00000001000000000000000000000000ffffffffffffffffffffffff"); }
+  static bignum_256 Gx() { return bn_from_hex("6b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296"); }
+  static bignum_256 Gy() { return bn_from_hex("4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5"); }
+};
+
+// ---- mgry.h / mgry_ops.h ----------------------------------------------------------------------
+template <class WBN = WBN256, class P = curve_nist_p256>
+struct wide_mgry_bignum {
+  using wide_bignum_type = WBN;
+  WBN n_;
+  wide_mgry_bignum() = default;
+  wide_mgry_bignum(WBN const& n) : n_(n) {}
+  static wide_mgry_bignum R() { return wide_mgry_bignum{WBN{bn_from_hex("00000000fffffffeffffffffffffffffffffffff000000000000000000000001")}}; }
+  static wide_mgry_bignum from_classical(WBN const& n) { wide_mgry_bignum r; detail::check(ecb200_from_classical(&r.n_, &n, 4, detail::kHostPack, nullptr)); return r; }
+  WBN to_classical() const { WBN r; detail::check(ecb200_to_classical(&r, &n_, 4, detail::kHostPack, nullptr)); return r; }
+  WBN const& wbn() const { return n_; }
+  WBN& wbn() { return n_; }
+};
+using WMBN = wide_mgry_bignum<>;
+static_assert(sizeof(WMBN) == 128, "layout");
+
+inline WMBN mgry_add(WMBN const& a, WMBN const& b) { WMBN r; detail::check(ecb200_mgry_add(&r, &a, &b, 4, detail::kHostPack, nullptr)); return r; }
+inline WMBN mgry_sub(WMBN const& a, WMBN const& b) { WMBN r; detail::check(ecb200_mgry_sub(&r, &a, &b, 4, detail::kHostPack, nullptr)); return r; }
+inline WMBN mgry_mul(WMBN const& a, WMBN const& b) { WMBN r; detail::check(ecb200_mgry_mul(&r, &a, &b, 4, detail::kHostPack, nullptr)); return r; }
+inline WMBN mgry_sqr(WMBN const& a) { WMBN r; detail::check(ecb200_mgry_sqr(&r, &a, 4, detail::kHostPack, nullptr)); return r; }
+template <std::size_t Count>
+inline WMBN mgry_shift_left(WMBN const& a) { static_assert(Count > 0 && Count <= 8); WMBN r; detail::check(ecb200_mgry_shift_left(&r, &a, int(Count), 4, detail::kHostPack, nullptr)); return r; }
+inline WMBN operator+(WMBN const& a, WMBN const& b) { return mgry_add(a, b); }
+inline WMBN operator-(WMBN const& a, WMBN const& b) { return mgry_sub(a, b); }
+inline WMBN operator*(WMBN const& a, WMBN const& b) { return mgry_mul(a, b); }
+
+// batch forms: npacks consecutive 4-lane packs per call
+inline void mgry_add(WMBN* out, WMBN const* a, WMBN const* b, std::size_t npacks) { detail::check(ecb200_mgry_add(out, a, b, 4 * npacks, detail::kHostPack, nullptr)); }
+inline void mgry_sub(WMBN* out, WMBN const* a, WMBN const* b, std::size_t npacks) { detail::check(ecb200_mgry_sub(out, a, b, 4 * npacks, detail::kHostPack, nullptr)); }
+inline void mgry_mul(WMBN* out, WMBN const* a, WMBN const* b, std::size_t npacks) { detail::check(ecb200_mgry_mul(out, a, b, 4 * npacks, detail::kHostPack, nullptr)); }
+inline void mgry_sqr(WMBN* out, WMBN const* a, std::size_t npacks) { detail::check(ecb200_mgry_sqr(out, a, 4 * npacks, detail::kHostPack, nullptr)); }
+
+// ---- gfp.h ----------------------------------------------------------------------------------------
+template <class WBN_ = WBN256, class P = curve_nist_p256>
+struct GFp {
+  using WBN = WBN_;
+  WMBN n_;
+  GFp() = default;
+  GFp(WMBN const& n) : n_(n) {}
+  static GFp one() { return GFp{WMBN::R()}; }
+  static GFp from_classical(WBN const& n) { return GFp{WMBN::from_classical(n)}; }
+  WBN to_classical() const { return n_.to_classical(); }
+  GFp inverse() const { GFp r; detail::check(ecb200_gfp_inverse(&r, this, 4, detail::kHostPack, nullptr)); return r; }
+  GFp sqr() const { return GFp{mgry_sqr(n_)}; }
+  GFp opposite() const { GFp r; detail::check(ecb200_gfp_opposite(&r, this, 4, detail::kHostPack, nullptr)); return r; }
+  WBN const& wbn() const { return n_.wbn(); }
+  WBN& wbn() { return n_.wbn(); }
+  WMBN const& wmbn() const { return n_; }
+};
+using gfp_p256 = GFp<>;
+static_assert(sizeof(gfp_p256) == 128, "layout");
+inline gfp_p256 operator+(gfp_p256 const& a, gfp_p256 const& b) { return gfp_p256{mgry_add(a.n_, b.n_)}; }
+inline gfp_p256 operator-(gfp_p256 const& a, gfp_p256 const& b) { return gfp_p256{mgry_sub(a.n_, b.n_)}; }
+inline gfp_p256 operator*(gfp_p256 const& a, gfp_p256 const& b) { return gfp_p256{mgry_mul(a.n_, b.n_)}; }
+template <std::size_t Count>
+inline gfp_p256 gfp_shift_left(gfp_p256 const& a) { return gfp_p256{mgry_shift_left<Count>(a.n_)}; }
+
+// ---- curve_point.h / jacobian_curve_point.h -----------------------------------------------------------
+template <class Curve = curve_nist_p256>
+struct wide_curve_point {
+  using WBN = WBN256;
+  WBN x_, y_;
+  wide_curve_point() = default;
+  wide_curve_point(WBN const& x, WBN const& y) : x_(x), y_(y) {}
+  WBN const& x() const { return x_; }
+  WBN const& y() const { return y_; }
+  WBN& x() { return x_; }
+  WBN& y() { return y_; }
+  friend bool operator==(wide_curve_point const& a, wide_curve_point const& b) { return a.x_ == b.x_ && a.y_ == b.y_; }
+};
+static_assert(sizeof(wide_curve_point<>) == 256, "layout");
+
+template <class Curve = curve_nist_p256>
+struct wide_jacobian_curve_point {
+  using gfp = gfp_p256;
+  gfp x_, y_, z_;
+  wide_jacobian_curve_point() = default;
+  static wide_jacobian_curve_point from_affine(wide_curve_point<Curve> const& pt) {
+    wide_jacobian_curve_point r;
+    detail::check(ecb200_from_affine(&r, &pt, 4, detail::kHostPack, nullptr));
+    return r;
+  }
+  wide_curve_point<Curve> to_affine() const {
+    wide_curve_point<Curve> r;
+    detail::check(ecb200_to_affine(&r, this, 4, detail::kHostPack, nullptr));
+    return r;
+  }
+  wide_jacobian_curve_point opposite() const { wide_jacobian_curve_point r = *this; r.y_ = y_.opposite(); return r; }
+  gfp& x() { return x_; }
+  gfp& y() { return y_; }
+  gfp& z() { return z_; }
+  gfp const& x() const { return x_; }
+  gfp const& y() const { return y_; }
+  gfp const& z() const { return z_; }
+  friend bool operator==(wide_jacobian_curve_point const& a, wide_jacobian_curve_point const& b) {
+    return a.x_.wbn() == b.x_.wbn() && a.y_.wbn() == b.y_.wbn() && a.z_.wbn() == b.z_.wbn();
+  }
+};
+static_assert(sizeof(wide_jacobian_curve_point<>) == 384, "must match the reference's x|y|z packs");
+
+// ---- curve_group.h ----------------------------------------------------------------------------------------
+template <class Curve>
+struct curve_group;
+template <>
+struct curve_group<curve_nist_p256> {
+  using Curve = curve_nist_p256;
+  using WBN = WBN256;
+  using BN = bignum_256;
+  using WCP = wide_curve_point<Curve>;
+  using WJCP = wide_jacobian_curve_point<Curve>;
+
+  static WCP WG() { return WCP{WBN{Curve::Gx()}, WBN{Curve::Gy()}}; }
+  static WJCP WJG() { return WJCP::from_affine(WG()); }
+
+  static WJCP DBLU(WJCP& P) { WJCP r, p; detail::check(ecb200_dblu(&p, &r, &P, 4, detail::kHostPack, nullptr)); P = p; return r; }
+  static WJCP ZADDU(WJCP& P, WJCP const& O) { WJCP r, p; detail::check(ecb200_zaddu(&p, &r, &P, &O, 4, detail::kHostPack, nullptr)); P = p; return r; }
+  static WJCP ZDAU(WJCP const& P, WJCP& Q) { WJCP r, q; detail::check(ecb200_zdau(&q, &r, &P, &Q, 4, detail::kHostPack, nullptr)); Q = q; return r; }
+  static WJCP ADD_Z2_1(WJCP const& A, WJCP const& B) { WJCP r; detail::check(ecb200_add_z2_1(&r, &A, &B, 4, detail::kHostPack, nullptr)); return r; }
+  static WJCP TRPLU(WJCP& P) { WJCP r, p; detail::check(ecb200_trplu(&p, &r, &P, 4, detail::kHostPack, nullptr)); P = p; return r; }
+
+  // Scalar multiplication, 4 scalars x 4 points (curve_group.h:189-218)
+  static WJCP scalar_mult(WBN const& x, WJCP P) { WJCP r; detail::check(ecb200_scalar_mult_p256(&r, &x, &P, 4, detail::kHostPack, nullptr)); return r; }
+  // Scalar multiplication, 1 scalar x 4 points (curve_group.h:221-251)
+  static WJCP scalar_mult_1s(BN const& x, WJCP P) {
+    WJCP r;
+    detail::check(ecb200_scalar_mult_p256_1s(&r, reinterpret_cast<const uint32_t*>(&x), &P, 4, detail::kHostPack, nullptr));
+    return r;
+  }
+  // Batch: npacks packs of 4 (scalar, point) pairs in one call -- the form the GPU is built for.
+  static void scalar_mult(WJCP* out, WBN const* x, WJCP const* P, std::size_t npacks) {
+    detail::check(ecb200_scalar_mult_p256(out, x, P, 4 * npacks, detail::kHostPack, nullptr));
+  }
+  static void scalar_mult_base(WJCP* out, WBN const* x, std::size_t npacks) {
+    detail::check(ecb200_scalar_mult_p256_base(out, x, 4 * npacks, detail::kHostPack, nullptr));
+  }
+  static void to_affine(WCP* out, WJCP const* J, std::size_t npacks) { detail::check(ecb200_to_affine(out, J, 4 * npacks, detail::kHostPack, nullptr)); }
+  static void from_affine(WJCP* out, WCP const* a, std::size_t npacks) { detail::check(ecb200_from_affine(out, a, 4 * npacks, detail::kHostPack, nullptr)); }
+};
+
+}  // namespace ecsimd
+
+// lib/scalar_mult_p256.cpp:12-14 -- the reference's one compiled entry point
+inline ecsimd::wide_jacobian_curve_point<ecsimd::curve_nist_p256> scalar_mult_p256(
+    ecsimd::WBN256 const& x, ecsimd::wide_jacobian_curve_point<ecsimd::curve_nist_p256> const& P) {
+  return ecsimd::curve_group<ecsimd::curve_nist_p256>::scalar_mult(x, P);
+}

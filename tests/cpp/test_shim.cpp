@@ -1,0 +1,86 @@
+// C++ drop-in check: the reference's own P-256 known-answer tests (tests/curve_group.cpp:38-173,
+// tests/curve_point.cpp:28-42), written against include/ecsimd_b200/ecsimd.hpp with the same
+// calls the reference tests make.  Built with plain g++ and linked to libecb200.so; run by
+// tests/test_gpu_cpp_shim.py on the GPU box.  Prints "ok <n>" or the first failure.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/ecsimd_b200/ecsimd.hpp"
+
+using namespace ecsimd;
+using Curve = curve_nist_p256;
+using CurveGroup = curve_group<Curve>;
+using WBN = WBN256;
+using WJCP = CurveGroup::WJCP;
+
+static int checks = 0;
+#define EXPECT_TRUE(c) do { ++checks; if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+static WBN set1(const char* hex) { return WBN{bn_from_hex(hex)}; }
+
+int main() {
+  if (ecb200_init(0) != 0) { std::printf("init failed: %s\n", ecb200_last_error()); return 2; }
+  {  // TEST(CurveGroup, DBLU)  tests/curve_group.cpp:38-52
+    auto WJG = CurveGroup::WJG();
+    const auto WJdblG = CurveGroup::DBLU(WJG);
+    EXPECT_TRUE(WJG.z().wbn() == WJdblG.z().wbn());
+    EXPECT_TRUE(WJG.to_affine() == CurveGroup::WG());
+    const auto WdblG = WJdblG.to_affine();
+    EXPECT_TRUE(WdblG.x() == set1("7cf27b188d034f7e8a52380304b51ac3c08969e277f21b35a60b48fc47669978"));
+    EXPECT_TRUE(WdblG.y() == set1("07775510db8ed040293d9ac69f7430dbba7dade63ce982299e04b79d227873d1"));
+  }
+  {  // TEST(CurveGroup, ZADDU)  :54-76   and TRPLU
+    auto WJG = CurveGroup::WJG();
+    const auto WJdblG = CurveGroup::DBLU(WJG);
+    const auto WJ3G = CurveGroup::ZADDU(WJG, WJdblG);
+    EXPECT_TRUE(WJG.z().wbn() == WJ3G.z().wbn());
+    const auto W3G = WJ3G.to_affine();
+    EXPECT_TRUE(W3G.x() == set1("5ecbe4d1a6330a44c8f7ef951d4bf165e6c6b721efada985fb41661bc6e7fd6c"));
+    EXPECT_TRUE(W3G.y() == set1("8734640c4998ff7e374b06ce1a64a2ecd82ab036384fb83d9a79b127a27d5032"));
+    auto G2 = CurveGroup::WJG();
+    EXPECT_TRUE(CurveGroup::TRPLU(G2) == WJ3G);
+  }
+  {  // TEST(CurveGroup, ZDAU)  :78-94   2*(2G) + G = 5G
+    auto WJG = CurveGroup::WJG();
+    const auto WJdblG = CurveGroup::DBLU(WJG);
+    const auto WJ5G = CurveGroup::ZDAU(WJdblG, WJG);
+    EXPECT_TRUE(WJG.z().wbn() == WJ5G.z().wbn());
+    const auto W5G = WJ5G.to_affine();
+    EXPECT_TRUE(W5G.x() == set1("51590b7a515140d2d784c85608668fdfef8c82fd1f5be52421554a0dc3d033ed"));
+    EXPECT_TRUE(W5G.y() == set1("e0c17da8904a727d8ae1bf36bf8a79260d012f00d4d80888d1d0bb44fda16da4"));
+  }
+  {  // TEST(CurveGroup, ScalarMult)  :117-173
+    const auto WJG = CurveGroup::WJG();
+    const auto k5 = bignum_256::from(5);
+    const auto r5 = CurveGroup::scalar_mult(WBN{k5}, WJG).to_affine();
+    EXPECT_TRUE(r5.x() == set1("51590b7a515140d2d784c85608668fdfef8c82fd1f5be52421554a0dc3d033ed"));
+    EXPECT_TRUE(CurveGroup::scalar_mult_1s(k5, WJG).to_affine() == r5);
+    const auto k = bn_from_hex("0bc1b1f28709decb543d9677d2cc9942348f6b984deff409430740942ff38827");
+    const auto J = scalar_mult_p256(WBN{k}, WJG);
+    // Jacobian/Montgomery representative as produced by the reference
+    EXPECT_TRUE(J.x().wbn() == set1("4c315298415aa6fee7a24142ca3d3e5687e9dd69c99c308ad361c4341445835a"));
+    EXPECT_TRUE(J.y().wbn() == set1("aa6cf5b34ea4ba14e76680e918bc8e19a38e60f112c49e92341052fd47611328"));
+    EXPECT_TRUE(J.z().wbn() == set1("d5488a3f8e4ab4c9de98a83a0f210fed2a47ca4224eaf4f73105386f504eca20"));
+    EXPECT_TRUE(CurveGroup::scalar_mult_1s(k, WJG) == J);
+  }
+  {  // TEST(JacobianCurvePoint, ToFromAffine)  tests/curve_point.cpp:28-42
+    const auto G = CurveGroup::WG();
+    EXPECT_TRUE(WJCP::from_affine(G).to_affine() == G);
+  }
+  {  // field ops behave like operators on GFp; batch == per-pack
+    const auto a = gfp_p256::from_classical(set1("6b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296"));
+    const auto b = gfp_p256::from_classical(set1("4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5"));
+    EXPECT_TRUE(((a + b) - b).wbn() == a.wbn());
+    EXPECT_TRUE((a * a).wbn() == a.sqr().wbn());
+    EXPECT_TRUE((a * a.inverse()).wbn() == gfp_p256::one().wbn());
+    EXPECT_TRUE((a + a).wbn() == gfp_shift_left<1>(a).wbn());
+    EXPECT_TRUE((a + a.opposite()).to_classical() == set1("0000000000000000000000000000000000000000000000000000000000000000"));
+    std::vector<WJCP> P(64, CurveGroup::WJG()), out(64);
+    std::vector<WBN> ks(64);
+    for (int i = 0; i < 64; i++) ks[i] = WBN{[&](int lane, int) { return bignum_256::from(uint64_t(4 * i + lane + 1)); }};
+    CurveGroup::scalar_mult(out.data(), ks.data(), P.data(), 64);
+    for (int i = 0; i < 64; i += 13) EXPECT_TRUE(out[i] == CurveGroup::scalar_mult(ks[i], P[i]));
+  }
+  std::printf("ok %d\n", checks);
+  return 0;
+}
