@@ -49,22 +49,50 @@ def parse():
 
 # ---- clocks during the timed region ---------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region (NVML, 20 ms period;
+    falls back to polling nvidia-smi)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.th = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                names.append(name)
+        return sm, self.max_sm, pw, names
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        out = [x.strip() for x in out]
+        names = [n for n, v in zip(("hw_slowdown", "sw_power_cap", "sw_thermal_slowdown", "hw_thermal_slowdown"), out[3:7])
+                 if v.lower().startswith("active")]
+        return float(out[0]), float(out[1]), float(out[2]), names
 
     def _run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self.rows.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -74,16 +102,11 @@ class ClockSampler:
         self.stop_flag.set()
         if self.th:
             self.th.join(timeout=10)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
-                "samples": len(self.rows), "reasons": sorted(reasons)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None,
+                "power_w_max": max((r[2] for r in self.rows), default=None), "samples": len(self.rows), "reasons": reasons,
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ---- CPU baselines (rank 0 only; checker libraries, never on the product path) ------------------
