@@ -67,12 +67,10 @@ __global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __
 
 // mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per lane
 // unless k_bcast (scalar_mult_1s: one scalar for all lanes).
-template <bool QUIRK, int MODE, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
-                                                     size_t n, int k_bcast);
-
-// One block of 384 threads per SM (12 warps), all warps kept in step by a barrier per ladder
-// iteration: the ~60 KB loop body is then fetched once per SM instead of once per warp.
+// The ladder kernel.  mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per
+// lane unless k_bcast (scalar_mult_1s: one scalar for all lanes).  One block of 512 threads per SM
+// (16 warps, 128 registers each), all warps kept in step by a barrier per ladder iteration: the
+// ~52 KB loop body is then fetched once per SM instead of once per warp.
 template <bool QUIRK, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restrict__ out, const void* __restrict__ k,
                                                                  const void* __restrict__ P, size_t n, int k_bcast) {
@@ -90,25 +88,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restric
   }
   const jac r = pt_scalar_mult<QUIRK, true>(kk.v, px, py);
   if (i0 < n) store_jac(out, n, i, r);
-}
-
-template <bool QUIRK, int MODE, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_scalar_mult(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P,
-                                                     size_t n, int k_bcast) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : S::load(k, n, i, 1, 0);
-  fe px, py;
-  if (MODE == 0) {
-    px = S::load(P, n, i, 3, 0);
-    py = S::load(P, n, i, 3, 1);
-  } else {
-    const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
-    px = fe_const(gx);
-    py = fe_const(gy);
-  }
-  const jac r = pt_scalar_mult<QUIRK>(kk.v, px, py);
-  store_jac(out, n, i, r);
 }
 
 template <bool QUIRK>
@@ -227,6 +206,73 @@ static int point_call(void* out1, void* out2, const void* A, const void* B, size
   return st.finish();
 }
 
+constexpr int kLadderThreads = 512;
+
+static int launch_ladder(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s) {
+  const unsigned blocks = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
+  if (mode == 0) {
+    if (q) k_scalar_mult_sync<true, 0, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+    else k_scalar_mult_sync<false, 0, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+  } else {
+    if (q) k_scalar_mult_sync<true, 1, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+    else k_scalar_mult_sync<false, 1, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+  }
+  ECB_LAUNCH_CHECK();
+  return ECB200_OK;
+}
+
+// Host-memory batches are cut into chunks of two full waves (2 x 148 SMs x 512 lanes) that rotate
+// over three internal streams: the PCIe copies and layout conversions of one chunk overlap the
+// ladder kernel of another, and the partial last wave of a chunk overlaps the next chunk's blocks.
+constexpr size_t kChunkLanes = 2 * 148 * (size_t)kLadderThreads;
+struct PipeStreams {
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  int device = -1;
+};
+static int pipe_streams(cudaStream_t** out) {
+  static thread_local PipeStreams ps;
+  int dev = 0;
+  ECB_CUDA(cudaGetDevice(&dev));
+  if (ps.device != dev) {
+    for (auto& st : ps.s) ECB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    ps.device = dev;
+  }
+  *out = ps.s;
+  return ECB200_OK;
+}
+
+static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, cudaStream_t user) {
+  const int L = layout_of(flags);
+  const bool q = quirk_on(flags);
+  cudaStream_t* ss = nullptr;
+  int rc = pipe_streams(&ss);
+  if (rc) return rc;
+  ECB_CUDA(cudaStreamSynchronize(user));  // host buffers are the caller's: order after its pending work
+  size_t c = 0;
+  for (size_t lo = 0; lo < n; lo += kChunkLanes, c++) {
+    const size_t m = (n - lo < kChunkLanes) ? n - lo : kChunkLanes;
+    cudaStream_t s = ss[c % 3];
+    Scratch sc(s);
+    void *rk, *rP = nullptr, *sk, *sP = nullptr, *so, *ro;
+    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&sk, operand_bytes(m, 1))) || (rc = sc.alloc(&so, operand_bytes(m, 3))) ||
+        (rc = sc.alloc(&ro, operand_bytes(m, 3))))
+      return rc;
+    // LANE and PACK4 are both contiguous per group of 4 lanes: a chunk is a byte range
+    ECB_CUDA(cudaMemcpyAsync(rk, (const char*)k + lo * 32, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
+    if ((rc = convert_to_soa(L, sk, rk, m, 1, s))) return rc;
+    if (mode == 0) {
+      if ((rc = sc.alloc(&rP, operand_bytes(m, 3))) || (rc = sc.alloc(&sP, operand_bytes(m, 3)))) return rc;
+      ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
+      if ((rc = convert_to_soa(L, sP, rP, m, 3, s))) return rc;
+    }
+    if ((rc = launch_ladder(so, sk, sP, mode, 0, m, q, s))) return rc;
+    if ((rc = convert_from_soa(L, ro, so, m, 3, s))) return rc;
+    ECB_CUDA(cudaMemcpyAsync((char*)out + lo * 96, ro, operand_bytes(m, 3), cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 3; i++) ECB_CUDA(cudaStreamSynchronize(ss[i]));
+  return ECB200_OK;
+}
+
 static int scalar_mult_call(void* out, const void* k, const void* P, int mode, int k_bcast, size_t n, uint32_t flags, void* stream) {
   int rc = check_common(n, flags);
   if (rc) return rc;
@@ -235,6 +281,8 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
     set_error("null pointer argument");
     return ECB200_ERR_ARG;
   }
+  if (!on_device(flags) && layout_of(flags) != L_SOA && !k_bcast && n > kChunkLanes)
+    return scalar_mult_host_pipelined(out, k, P, mode, n, flags, (cudaStream_t)stream);
   Staged st((cudaStream_t)stream, flags, n);
   const void *dk = nullptr, *dP = nullptr;
   void* dout = nullptr;
@@ -246,34 +294,7 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   } else if ((rc = st.in(k, 1, &dk))) return rc;
   if (mode == 0 && (rc = st.in(P, 3, &dP))) return rc;
   if ((rc = st.out(out, 3, &dout))) return rc;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
-  const bool q = quirk_on(flags);
-  static const int minb = [] { const char* e = getenv("ECB200_SM_MINB"); return e ? atoi(e) : 512; }();  // development knob
-  if (mode == 0 && minb >= 384) {
-    const unsigned b2 = (unsigned)((n + minb - 1) / minb);
-    if (minb == 384) {
-      if (q) k_scalar_mult_sync<true, 0, 384><<<b2, 384, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-      else k_scalar_mult_sync<false, 0, 384><<<b2, 384, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    } else {
-      if (q) k_scalar_mult_sync<true, 0, 512><<<b2, 512, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-      else k_scalar_mult_sync<false, 0, 512><<<b2, 512, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    }
-  } else if (mode == 0) {
-    if (minb == 4) {
-      if (q) k_scalar_mult<true, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-      else k_scalar_mult<false, 0, 4><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    } else if (minb == 5) {
-      if (q) k_scalar_mult<true, 0, 5><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-      else k_scalar_mult<false, 0, 5><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    } else {
-      if (q) k_scalar_mult<true, 0, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-      else k_scalar_mult<false, 0, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    }
-  } else {
-    if (q) k_scalar_mult<true, 1, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-    else k_scalar_mult<false, 1, 3><<<blocks, 128, 0, st.s>>>(dout, dk, dP, n, k_bcast);
-  }
-  ECB_LAUNCH_CHECK();
+  if ((rc = launch_ladder(dout, dk, dP, mode, k_bcast, n, quirk_on(flags), st.s))) return rc;
   return st.finish();
 }
 

@@ -64,8 +64,8 @@ __device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O, MD& md) {
 
 // ZDAU core on bare coordinates: (X1,Y1) <- 2*(X1,Y1) + (X2,Y2); (X2,Y2) <- the same
 // point (X2,Y2) re-scaled to the new common Z; Z <- new Z.
-template <bool QUIRK, class MD>
-__device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z, MD& md) {
+template <bool QUIRK, class MD, int MIDSYNC = 0>
+__device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z, MD& md, int grp = 0) {
   const fe dx = fp_sub(X1, X2);
   const fe dy = fp_sub(Y1, Y2);
   const fe Cp = fp_sqr<QUIRK>(dx, md);
@@ -84,6 +84,7 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe W1 = fp_mul(X3pc, C4, md);
   const fe W2 = fp_mul(W1p, C4, md);
   const fe W12 = fp_add(W1, W2, md);
+  if (MIDSYNC) { if (grp == 1) asm volatile("bar.sync 0;" ::: "memory"); }
   const fe ym = fp_sub(Y3p, A2);
   const fe yp = fp_add(Y3p, A2, md);
   const fe D = fp_sqr<QUIRK>(ym, md);

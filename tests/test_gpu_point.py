@@ -157,3 +157,21 @@ def test_full_size_scalar_mult(eng, orc):
     # lanes hit by the squaring defect anywhere along either ladder may differ: at most a handful
     assert mism.sum() <= 64, mism.sum()
     assert a0.shape == (n, 16)
+
+
+def test_scalar_mult_host_pipelined_chunks(eng, orc):
+    """host batches above one chunk (2 waves = 151 552 lanes) go through the multi-stream pipelined
+    path: ragged last chunk, pack4 layout, result independent of the chunking"""
+    n = 151552 * 2 + 260
+    base = _points(orc, 256, 0xEC51D009)
+    P = np.tile(base, (n // 256 + 1, 1))[:n]
+    k = raw256(0xEC51D00A, n)
+    got = eng.pack4_to_lane(eng.scalar_mult(eng.lane_to_pack4(k, 1), eng.lane_to_pack4(P, 3), layout="pack4"), 3)
+    idx = np.concatenate([np.arange(0, 64), np.arange(151552 - 32, 151552 + 32), np.arange(2 * 151552 - 32, n)])
+    assert np.array_equal(got[idx], orc.scalar_mult(k[idx], P[idx]))
+    # the same lanes through the single-shot path (small batch) agree
+    assert np.array_equal(got[:1000], eng.scalar_mult(k[:1000], P[:1000]))
+    # base-point mode through the same path
+    gotb = eng.scalar_mult_base(k)
+    GJ = np.repeat(orc.from_affine(np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)), len(idx), axis=0)
+    assert np.array_equal(gotb[idx], orc.scalar_mult(k[idx], GJ))

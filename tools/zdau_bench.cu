@@ -52,6 +52,28 @@ __device__ __forceinline__ void zdau_v(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z) {
   X1 = X3; Y1 = Y3; X2 = X2n; Y2 = Y2n; Z = Z3;
 }
 
+// two phase groups per sub-partition, half a step apart (lockstep vs pipe mixing)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_zdau_skew2(uint32_t* io, int iters) {
+  const size_t t = (size_t)threadIdx.x + (size_t)blockIdx.x * blockDim.x;
+  const int grp = ((threadIdx.x >> 5) >> 2) & 1;
+  fe v[5];
+  Lazy md;
+  for (int c = 0; c < 5; c++)
+    for (int i = 0; i < 8; i++) v[c].v[i] = io[t * 40 + c * 8 + i];
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    const uint32_t sw = (v[0].v[0] >> (it & 31)) & 1u;
+    fe_cswap(sw, v[0], v[2]);
+    fe_cswap(sw, v[1], v[3]);
+    if (grp == 0) asm volatile("bar.sync 0;" ::: "memory");
+    pt_zdau_xy<BENCH_QUIRK, Lazy, 1>(v[0], v[1], v[2], v[3], v[4], md, grp);
+  }
+  if (md.flagged()) v[0].v[0] ^= 1;
+  for (int c = 0; c < 5; c++)
+    for (int i = 0; i < 8; i++) io[t * 40 + c * 8 + i] = v[c].v[i];
+}
+
 template <bool CALLS, bool SYNC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_zdau(uint32_t* io, int iters) {
   const size_t t = (size_t)threadIdx.x + (size_t)blockIdx.x * blockDim.x;
@@ -107,6 +129,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
   run("inline_128x3", k_zdau<false, false, 128, 3>, 128, 3, d, iters);
   run("inline_sync_384x1", k_zdau<false, true, 384, 1>, 384, 1, d, iters);
+  run("skew2_512x1", k_zdau_skew2<512>, 512, 1, d, iters);
   run("inline_sync_512x1", k_zdau<false, true, 512, 1>, 512, 1, d, iters);
 
 #if VARIANT_CALLS
