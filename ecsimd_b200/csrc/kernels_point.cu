@@ -109,6 +109,30 @@ __global__ void __launch_bounds__(128) k_to_affine(void* __restrict__ xy, const 
   S::store(xy, n, i, 2, 1, fp_to_classical(fp_mul(a.y, iz3)));
 }
 
+// wide_curve_point::from_x / curve_group::compute_y (curve_point_ops.h:12-22, curve_group.h:43-58):
+// y = sqrt(x^3 - 3x + b) with sqrt = pow((p+1)/4) (gfp.h:46-54) through the reference's LSB-first
+// square-and-multiply (mgry_ops.h:44-86, same sequence of squarings), then the check r^2 == y^2.
+// ok[i] = 1 iff lane i has a square root (the reference answers per 4-lane pack: all four or none).
+template <bool QUIRK>
+__global__ void __launch_bounds__(128) k_from_x(void* __restrict__ y, uint8_t* __restrict__ ok, const void* __restrict__ x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const fe xm = fp_from_classical(S::load(x, n, i, 1, 0));
+  const fe xpow3 = fp_mul(fp_sqr<QUIRK>(xm), xm);
+  const fe x3 = fp_add(fp_shl1(xm), xm);
+  const fe ypow2 = fp_sub(fp_add(xpow3, fe_BM()), x3);
+  // (p+1)/4 = 2^254 - 2^222 + 2^190 + 2^94
+  const uint32_t e[8] = {0u, 0u, 0x40000000u, 0u, 0u, 0x40000000u, 0xc0000000u, 0x3fffffffu};
+  fe res = fe_R(), base = ypow2;
+#pragma unroll 1
+  for (int b = 0; b < 254; b++) {
+    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base);
+    if (b < 253) base = fp_sqr<QUIRK>(base);
+  }
+  ok[i] = fe_eq(fp_sqr<QUIRK>(res), ypow2) ? 1 : 0;
+  S::store(y, n, i, 1, 0, fp_to_classical(res));
+}
+
 __global__ void __launch_bounds__(256) k_from_affine(void* __restrict__ J, const void* __restrict__ xy, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -341,6 +365,26 @@ int ecb200_from_affine(void* outJ, const void* xy, size_t n, uint32_t flags, voi
   if ((rc = st.out(outJ, 3, &dout))) return rc;
   k_from_affine<<<(unsigned)((n + 255) / 256), 256, 0, st.s>>>(dout, din, n);
   ECB_LAUNCH_CHECK();
+  return st.finish();
+}
+
+int ecb200_from_x(void* y, uint8_t* ok, const void* x, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  if (!y || !ok || !x) { set_error("null pointer argument"); return ECB200_ERR_ARG; }
+  Staged st((cudaStream_t)stream, flags, n);
+  const void* din = nullptr;
+  void* dout = nullptr;
+  void* dok = ok;
+  if ((rc = st.in(x, 1, &din))) return rc;
+  if ((rc = st.out(y, 1, &dout))) return rc;
+  if (!on_device(flags) && (rc = st.sc.alloc(&dok, n))) return rc;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (quirk_on(flags)) k_from_x<true><<<blocks, 128, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
+  else k_from_x<false><<<blocks, 128, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
+  ECB_LAUNCH_CHECK();
+  if (!on_device(flags)) ECB_CUDA(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st.s));
   return st.finish();
 }
 

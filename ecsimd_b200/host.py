@@ -137,6 +137,16 @@ def to_affine(J, layout="lane", quirk=True):
     return _run("ecb200_to_affine", [2], [J], 3, layout, quirk)
 
 
+def from_x(x, layout="lane", quirk=True):
+    """wide_curve_point::from_x: y = sqrt(x^3 - 3x + b)  curve_point_ops.h:12-22; -> (y, ok[n] uint8)"""
+    x = _in(x)
+    n = lanes_of(x, layout, 1)
+    y = np.zeros(_shape(layout, n, 1), np.uint32)
+    ok = np.zeros(n, np.uint8)
+    capi.call("ecb200_from_x", capi._p(y), capi._p(ok), capi._p(x), n, _flags(layout, quirk), None)
+    return y, ok
+
+
 def synth_values(seed, start, n, kind, layout="lane"):
     out = np.zeros(_shape(layout, n, 1), np.uint32)
     capi.call("ecb200_synth_values", capi._p(out), seed, start, kind, n, LAYOUTS[layout] | MEM_HOST, None)

@@ -141,6 +141,12 @@ int ecb200_from_affine(void* outJ, const void* xy, size_t n, uint32_t flags, voi
 /* xy = J.to_affine()                                   jacobian_curve_point.h:33-42 */
 int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* stream);
 
+/* y = wide_curve_point::from_x(x).y(): point decompression, y = sqrt(x^3 - 3x + b) (classical x in,
+ * classical y out)   curve_point_ops.h:12-22, curve_group.h:43-58, gfp.h:46-54.
+ * ok[i] (n bytes, same memory space as the other pointers) = 1 iff lane i has a square root; the
+ * reference's std::optional answers per 4-lane pack: a pack is valid iff all four ok bytes are 1. */
+int ecb200_from_x(void* y, uint8_t* ok, const void* x, size_t n, uint32_t flags, void* stream);
+
 /* ---- synthetic inputs, generated on the device (bench / large parity runs) ------ */
 /* value i = 4 x splitmix64 words of counter (seed * 0x100000001B3 + 4*(start+i) + limb);
  * kind 0: raw 256 bits (scalars); kind 1: canonical field element (minus p once if >= p). */

