@@ -265,25 +265,30 @@ def simulate(ir, env):
 # Every 32x32+64 step is one IMAD.WIDE.U32(.X): 4.1 clk of the FMA-heavy pipe per warp on B200
 # (measured, tools/microbench_mix.py), so the schedules below use exactly 64 (mul) / 36 (sqr)
 # of them and keep everything else on plain IADD3 carry chains.
+# Order matters: a chain that ends on an already used pair hands its carry-out to the NEXT pair
+# as a one-instruction "deposit" (addc into a still untouched register), and it is scheduled
+# before any product touches that next pair; the chain that later ends there still absorbs its
+# own carry, because a*b + deposit + carry < 2^64.  So the 64 products need 7 deposits and no
+# extra carry-propagation chain.
 MUL_E_CHAINS = [
-    [(0, 0, 0), (2, 0, 2), (4, 0, 4), (6, 0, 6)],
-    [(2, 2, 0), (4, 2, 2), (6, 2, 4), (8, 2, 6)],
-    [(2, 1, 1), (4, 1, 3), (6, 1, 5), (8, 1, 7), (10, 3, 7)],
-    [(4, 4, 0), (6, 4, 2), (8, 4, 4), (10, 4, 6), (12, 5, 7)],
-    [(4, 3, 1), (6, 3, 3), (8, 3, 5), (10, 5, 5), (12, 6, 6), (14, 7, 7)],
-    [(6, 6, 0), (8, 6, 2), (10, 6, 4), (12, 7, 5)],
-    [(6, 5, 1), (8, 5, 3), (10, 7, 3)],
-    [(8, 7, 1)],
+    [(0, 0, 0), (2, 0, 2), (4, 0, 4), (6, 0, 6)],                                  # ends fresh on pair 6
+    [(2, 2, 0), (4, 2, 2), (6, 2, 4), (8, 2, 6)],                                  # ends fresh on 8
+    [(8, 7, 1)],                                                                   # used pair 8 -> deposit on 10
+    [(6, 5, 1), (8, 5, 3), (10, 7, 3)],                                            # ends on 10 (deposit only)
+    [(2, 1, 1), (4, 1, 3), (6, 1, 5), (8, 1, 7), (10, 3, 7)],                      # used 10 -> deposit on 12
+    [(6, 6, 0), (8, 6, 2), (10, 6, 4), (12, 7, 5)],                                # ends on 12 (deposit only)
+    [(4, 4, 0), (6, 4, 2), (8, 4, 4), (10, 4, 6), (12, 5, 7)],                     # used 12 -> deposit on 14
+    [(4, 3, 1), (6, 3, 3), (8, 3, 5), (10, 5, 5), (12, 6, 6), (14, 7, 7)],         # ends on 14 (top)
 ]
 MUL_O_CHAINS = [
-    [(1, 0, 1), (3, 0, 3), (5, 0, 5), (7, 0, 7)],
-    [(1, 1, 0), (3, 1, 2), (5, 1, 4), (7, 1, 6), (9, 3, 6)],
-    [(3, 2, 1), (5, 2, 3), (7, 2, 5), (9, 2, 7), (11, 4, 7)],
-    [(3, 3, 0), (5, 3, 2), (7, 3, 4), (9, 5, 4), (11, 5, 6), (13, 7, 6)],
-    [(5, 4, 1), (7, 4, 3), (9, 4, 5), (11, 6, 5), (13, 6, 7)],
-    [(5, 5, 0), (7, 5, 2), (9, 7, 2), (11, 7, 4)],
-    [(7, 6, 1), (9, 6, 3)],
-    [(7, 7, 0)],
+    [(1, 0, 1), (3, 0, 3), (5, 0, 5), (7, 0, 7)],                                  # ends fresh on 7
+    [(7, 7, 0)],                                                                   # used 7 -> deposit on 9
+    [(7, 6, 1), (9, 6, 3)],                                                        # ends on 9 (deposit only)
+    [(1, 1, 0), (3, 1, 2), (5, 1, 4), (7, 1, 6), (9, 3, 6)],                       # used 9 -> deposit on 11
+    [(5, 5, 0), (7, 5, 2), (9, 7, 2), (11, 7, 4)],                                 # ends on 11 (deposit only)
+    [(3, 2, 1), (5, 2, 3), (7, 2, 5), (9, 2, 7), (11, 4, 7)],                      # used 11 -> deposit on 13
+    [(5, 4, 1), (7, 4, 3), (9, 4, 5), (11, 6, 5), (13, 6, 7)],                     # ends on 13 (deposit only)
+    [(3, 3, 0), (5, 3, 2), (7, 3, 4), (9, 5, 4), (11, 5, 6), (13, 7, 6)],          # used 13 -> deposit on word 15
 ]
 # cross products a_i*a_j, i<j, of the squaring
 SQR_E_CHAINS = [
@@ -315,9 +320,9 @@ def _check_cover(chains_e, chains_o, square):
 
 
 def emit_products(g, chains_e, chains_o, xa, xb, tops):
-    """Emit the product chains.  Returns (touched registers, captured carry words {position: [regs]})."""
-    touched = set()
-    caps = {}
+    """Emit the product chains.  Returns the set of registers that hold a value afterwards."""
+    touched = set()       # registers holding a value
+    deposit_only = set()  # ... that so far hold nothing but a deposited carry (0/1)
 
     def R(acc, w):
         return "%s%d" % (acc, w)
@@ -338,17 +343,22 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops):
                     # carry-setting multiply-add so that ptxas keeps it instead of recomputing it
                     g.madw(lo, hi, xa % i, xb % j, False, True, fresh=(True, True))
                 else:
-                    # the carry out of the last step is dropped only where it cannot exist
-                    safe_end = last and (all(fresh) or w == top)
+                    # the carry out of the last step is dropped only where it cannot exist: on a pair that
+                    # holds at most a deposited carry, or on the top pair of the accumulator
+                    nearly_fresh = fresh[1] and (fresh[0] or lo in deposit_only)
+                    safe_end = last and (nearly_fresh or w == top)
                     g.madw(lo, hi, xa % i, xb % j, cin, not safe_end, fresh=fresh)
                     cin = True
                     if last and not safe_end:
-                        c = "c%s%d" % (acc, w + 2)
-                        g.cap(c, True)
-                        caps.setdefault(w + 2, []).append(c)
+                        dep = R(acc, w + 2)
+                        assert dep not in touched, "deposit target %s already in use: reorder the chains" % dep
+                        g.cap(dep, True)
+                        touched.add(dep)
+                        deposit_only.add(dep)
                 touched.add(lo); touched.add(hi)
+                deposit_only.discard(lo)
             g.end()
-    return touched, caps
+    return touched
 
 
 def emit_reduction(g, T):
@@ -407,23 +417,13 @@ def emit_reduction(g, T):
 def gen_mul():
     _check_cover(MUL_E_CHAINS, MUL_O_CHAINS, False)
     g = Emit()
-    touched, caps = emit_products(g, MUL_E_CHAINS, MUL_O_CHAINS, "a%d", "b%d", {"e": 14, "o": None})
+    touched = emit_products(g, MUL_E_CHAINS, MUL_O_CHAINS, "a%d", "b%d", {"e": 14, "o": None})
     # merge T = E + O (word 0 is e0 itself)
     g.begin()
     for w in range(1, 16):
         ev = "e%d" % w if "e%d" % w in touched else 0
         ov = "o%d" % w if "o%d" % w in touched else 0
         g.add32("t%d" % w, ev, ov, w > 1, w < 15)
-    g.end()
-    # the carries captured at chain ends
-    lo = min(caps)
-    g.begin()
-    first = True
-    for w in range(lo, 16):
-        cs = caps.get(w, [])
-        assert len(cs) <= 1
-        g.add32("t%d" % w, "t%d" % w, cs[0] if cs else 0, not first, w < 15)
-        first = False
     g.end()
     emit_reduction(g, ["e0"] + ["t%d" % w for w in range(1, 16)])
     return g
@@ -432,8 +432,7 @@ def gen_mul():
 def gen_sqr():
     _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
     g = Emit()
-    touched, caps = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None})
-    assert not caps
+    touched = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None})
     # cross sum S = E + O: words 1..14, carry into word 15
     g.begin()
     for w in range(1, 15):

@@ -233,14 +233,15 @@ __global__ void __launch_bounds__(256) k_microbench(uint32_t* __restrict__ out, 
 
 // Generic pipe-mix probe: per step NW x IMAD.WIDE.U32, NL x IMAD (lo), NH x IMAD.HI.U32 and
 // NA x (IADD3 + IADD3.X) pairs, every op on its own dependent chain (8 chains per kind).
-template <int NW, int NL, int NH, int NA>
+template <int NW, int NL, int NH, int NA, int NM = 0>
 __global__ void __launch_bounds__(256) k_mix(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t wl[8], wh[8], l[8], h[8], al[8], ah[8];
+  uint32_t wl[8], wh[8], l[8], h[8], al[8], ah[8], ml[8], mh[8];
   const uint32_t y = in[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     wl[j] = in[j] + tid; wh[j] = ~wl[j]; l[j] = wl[j] * 3u; h[j] = wl[j] * 5u; al[j] = wl[j] * 7u; ah[j] = wl[j] * 9u;
+    ml[j] = wl[j] * 11u; mh[j] = wl[j] * 13u;
   }
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
@@ -251,13 +252,14 @@ __global__ void __launch_bounds__(256) k_mix(uint32_t* __restrict__ out, const u
         if (j < NW) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(wl[j & 7]), "+r"(wh[j & 7]) : "r"(wh[(j + 3) & 7]), "r"(y));
         if (j < NL) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(l[j & 7]) : "r"(y), "r"(l[(j + 3) & 7]));
         if (j < NH) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(h[j & 7]) : "r"(y), "r"(h[(j + 3) & 7]));
+        if (j < NM) asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(ml[j & 7]), "=r"(mh[j & 7]) : "r"(mh[(j + 3) & 7] | 1u), "r"(ml[(j + 5) & 7]));
         if (j < NA) asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(al[j & 7]), "+r"(ah[j & 7]) : "r"(ah[(j + 3) & 7]), "r"(al[(j + 5) & 7]));
       }
     }
   }
   uint32_t t = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) t += wl[j] ^ wh[j] ^ l[j] ^ h[j] ^ al[j] ^ ah[j];
+  for (int j = 0; j < 8; j++) t += wl[j] ^ wh[j] ^ l[j] ^ h[j] ^ al[j] ^ ah[j] ^ ml[j] ^ mh[j];
   out[tid] = t;
 }
 
@@ -266,7 +268,8 @@ struct MixCombo { int nw, nl, nh, na; void (*fn)(uint32_t*, const uint32_t*, int
 static const MixCombo g_mix[] = {
     MIX(8, 0, 0, 0), MIX(0, 8, 0, 0), MIX(0, 0, 8, 0), MIX(0, 8, 8, 0), MIX(0, 0, 0, 8), MIX(8, 0, 0, 4), MIX(8, 0, 0, 8),
     MIX(8, 0, 0, 12), MIX(0, 8, 8, 8), MIX(0, 8, 0, 8), MIX(0, 0, 8, 8), MIX(8, 8, 0, 0), MIX(8, 0, 8, 0), MIX(4, 8, 8, 8),
-    MIX(8, 4, 0, 8), MIX(8, 0, 4, 8), MIX(4, 0, 0, 12), MIX(0, 12, 0, 0), MIX(0, 12, 0, 12)};
+    MIX(8, 4, 0, 8), MIX(8, 0, 4, 8), MIX(4, 0, 0, 12), MIX(0, 12, 0, 0), MIX(0, 12, 0, 12),
+    {0, 0, 0, 0, k_mix<0, 0, 0, 0, 8>}, {0, 0, 0, 8, k_mix<0, 0, 0, 8, 8>}, {0, 0, 0, 12, k_mix<0, 0, 0, 12, 8>}, {4, 0, 0, 8, k_mix<4, 0, 0, 8, 4>}};
 static const int g_nmix = (int)(sizeof(g_mix) / sizeof(g_mix[0]));
 
 template <int L, int OP, bool Q>
