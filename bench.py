@@ -339,6 +339,27 @@ def main():
                                       "lanes": nb, "ms": t_big, "mulmod_per_s": nb / t_big * 1e3, "algorithmic_bytes_per_lane": 96},
                "mulmod_register_resident": {"mulmod_per_s": n * 1024 / t_chain * 1e3, "TMAC32_per_s": n * 1024 * 64 / t_chain * 1e3 / 1e12,
                                             "frac_of_imad_peak": n * 1024 * 64 / t_chain * 1e3 / peak_wide}}
+        # BASELINE configs[1]: point add + double over 2^22 points (TRPLU = DBLU + ZADDU, then ZDAU on the pair)
+        n2 = 1 << 22
+        r2 = dev.synth_values(dev.empty(n2, 1), SEED_POINTS, 0, n2, 0)
+        J2 = dev.scalar_mult_base(dev.empty(n2, 3), r2, n2)
+        P2 = dev.from_affine(dev.empty(n2, 3), dev.to_affine(dev.empty(n2, 2), J2, n2), n2)
+        Q2, R2, O2 = dev.empty(n2, 3), dev.empty(n2, 3), dev.empty(n2, 3)
+        dev.trplu(Q2, R2, P2, n2); torch.cuda.synchronize()
+        t_trplu = timed(lambda: dev.trplu(Q2, R2, P2, n2), 3)
+        t_zdau = timed(lambda: dev.zdau(O2, J2, R2, Q2, n2), 3)
+        aux["point_ops_2^22"] = {
+            "trplu": {"ms": t_trplu, "points_per_s": n2 / t_trplu * 1e3, "GBps": n2 * 288 / t_trplu * 1e3 / 1e9, "TMAC32_per_s": n2 * 636 / t_trplu * 1e3 / 1e12},
+            "zdau": {"ms": t_zdau, "points_per_s": n2 / t_zdau * 1e3, "GBps": n2 * 384 / t_zdau * 1e3 / 1e9, "TMAC32_per_s": n2 * 828 / t_zdau * 1e3 / 1e12},
+            "note": "algorithmic: TRPLU 6M+7S = 636 MAC32, 96 B in + 192 B out; ZDAU 9M+7S = 828 MAC32, 192 B in + 192 B out"}
+        del r2, J2, P2, Q2, R2, O2
+        # BASELINE configs[3]: generator, 2^24 scalars (same ladder with P = G: the only form that keeps the reference's (X:Y:Z))
+        n4 = 1 << 24
+        k4 = dev.synth_values(dev.empty(n4, 1), SEED_SCALARS, 0, n4, 0)
+        O4 = dev.empty(n4, 3)
+        t_base = timed(lambda: dev.scalar_mult_base(O4, k4, n4), 1)
+        aux["scalar_mult_base_2^24"] = {"ms": t_base, "scalar_mults_per_s": n4 / t_base * 1e3, "frac_of_imad_peak": n4 * MAC32_PER_SCALAR_MULT / t_base * 1e3 / peak_wide}
+        del k4, O4
         del a, b, o1, flush
 
     if rank != 0:

@@ -34,39 +34,43 @@ __device__ __forceinline__ void store_jac(void* p, size_t n, size_t i, const jac
 
 enum PointOp : int { PO_DBLU, PO_ZADDU, PO_ZDAU, PO_ADDZ21, PO_TRPLU };
 
-template <int OP, bool QUIRK>
-__global__ void __launch_bounds__(128) k_point(void* __restrict__ out1, void* __restrict__ out2, const void* __restrict__ A,
-                                               const void* __restrict__ B, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// One point op per thread.  The op runs in Lazy mode (no branches on the 2^-32 cases); a lane that
+// flagged one is re-run from its (reloaded) inputs in Exact mode by an out-of-line copy.
+template <int OP, bool QUIRK, class MD>
+__device__ __forceinline__ void point_compute(const void* A, const void* B, size_t n, size_t i, MD& md, jac& r, jac& w) {
   jac a = load_jac(A, n, i);
+  // r: returned point, w: rewritten operand
+  if (OP == PO_DBLU) { r = pt_dblu<QUIRK>(a, md); w = a; }
+  else if (OP == PO_TRPLU) { r = pt_trplu<QUIRK>(a, md); w = a; }
+  else if (OP == PO_ZADDU) { const jac b = load_jac(B, n, i); r = pt_zaddu<QUIRK>(a, b, md); w = a; }
+  else if (OP == PO_ZDAU) { jac q = load_jac(B, n, i); r = pt_zdau<QUIRK>(a, q, md); w = q; }
+  else { const fe bx = S::load(B, n, i, 3, 0), by = S::load(B, n, i, 3, 1); r = pt_add_z2_1<QUIRK>(a, bx, by, md); w = r; }
+}
+template <int OP>
+__device__ __forceinline__ void point_store(void* out1, void* out2, size_t n, size_t i, const jac& r, const jac& w) {
+  if (OP == PO_ADDZ21) store_jac(out1, n, i, r);
+  else { store_jac(out1, n, i, w); store_jac(out2, n, i, r); }
+}
+template <int OP, bool QUIRK>
+__device__ __noinline__ void point_op_exact(void* out1, void* out2, const void* A, const void* B, size_t n, size_t i) {
   Exact md;
-  if (OP == PO_DBLU) {
-    const jac r = pt_dblu<QUIRK>(a, md);
-    store_jac(out1, n, i, a);
-    store_jac(out2, n, i, r);
-  } else if (OP == PO_TRPLU) {
-    const jac r = pt_trplu<QUIRK>(a, md);
-    store_jac(out1, n, i, a);
-    store_jac(out2, n, i, r);
-  } else if (OP == PO_ZADDU) {
-    const jac b = load_jac(B, n, i);
-    const jac r = pt_zaddu<QUIRK>(a, b, md);
-    store_jac(out1, n, i, a);
-    store_jac(out2, n, i, r);
-  } else if (OP == PO_ZDAU) {
-    jac q = load_jac(B, n, i);
-    const jac r = pt_zdau<QUIRK>(a, q, md);
-    store_jac(out1, n, i, q);
-    store_jac(out2, n, i, r);
-  } else if (OP == PO_ADDZ21) {
-    const fe bx = S::load(B, n, i, 3, 0), by = S::load(B, n, i, 3, 1);
-    store_jac(out1, n, i, pt_add_z2_1<QUIRK>(a, bx, by, md));
-  }
+  jac r, w;
+  point_compute<OP, QUIRK>(A, B, n, i, md, r, w);
+  point_store<OP>(out1, out2, n, i, r, w);
 }
 
-// mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per lane
-// unless k_bcast (scalar_mult_1s: one scalar for all lanes).
+template <int OP, bool QUIRK>
+__global__ void __launch_bounds__(128) k_point(void* out1, void* out2, const void* A, const void* B, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Lazy md;
+  jac r, w;
+  point_compute<OP, QUIRK>(A, B, n, i, md, r, w);
+  // nothing has been stored yet, so the exact re-run still sees the inputs even if outputs alias them
+  if (__builtin_expect(md.flagged(), 0)) point_op_exact<OP, QUIRK>(out1, out2, A, B, n, i);
+  else point_store<OP>(out1, out2, n, i, r, w);
+}
+
 // The ladder kernel.  mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per
 // lane unless k_bcast (scalar_mult_1s: one scalar for all lanes).  One block of 512 threads per SM
 // (16 warps, 128 registers each), all warps kept in step by a barrier per ladder iteration: the
