@@ -95,16 +95,17 @@ struct Lazy {
 // The single conditional subtraction every modular op ends with (sub_if_above, sub.h:46-69):
 // given the 257-bit value (c:s), return it minus p if it is >= p.  c == 1 always subtracts;
 // c == 0 subtracts only if s >= p, which needs s7 == 0xffffffff (probability 2^-32 on uniform
-// data): that case branches to an exact comparison, everything else is one 8-word add of
-// (2^256 - p) & mask = {sub, 0, 0, mask, mask, mask, mask<<1, 0}.
+// data): that case branches to an exact comparison (or is only flagged, Lazy mode); everything else
+// is one 8-word subtraction of p & mask.
 __device__ __forceinline__ fe fp_add_k(const fe& s, uint32_t sub) {
-  const uint32_t mask = 0u - sub, k6 = mask + mask;
+  // s - (p & mask), p & mask = {mask, mask, mask, 0, 0, 0, sub, mask}   (mod 2^256: the borrow out cancels c)
+  const uint32_t mask = 0u - sub;
   fe r;
-  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, 0; addc.cc.u32 %2, %10, 0; addc.cc.u32 %3, %11, %17; "
-      "addc.cc.u32 %4, %12, %17; addc.cc.u32 %5, %13, %17; addc.cc.u32 %6, %14, %18; addc.u32 %7, %15, 0;"
+  asm("sub.cc.u32 %0, %8, %17; subc.cc.u32 %1, %9, %17; subc.cc.u32 %2, %10, %17; subc.cc.u32 %3, %11, 0; "
+      "subc.cc.u32 %4, %12, 0; subc.cc.u32 %5, %13, 0; subc.cc.u32 %6, %14, %16; subc.u32 %7, %15, %17;"
       : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
       : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
-        "r"(sub), "r"(mask), "r"(k6));
+        "r"(sub), "r"(mask));
   return r;
 }
 __device__ __forceinline__ fe fp_reduce_once(const fe& s, uint32_t c, Exact&) {
