@@ -28,8 +28,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner out of it
-os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: keep NCCL's banner (printed to stdout when NCCL_DEBUG is set,
+# as it is on the GPU boxes) out of it
+os.environ.pop("NCCL_DEBUG", None)
+os.environ["NCCL_DEBUG_FILE"] = os.devnull
 
 LANES_PER_GPU = 1 << 20
 MAC32_PER_SCALAR_MULT = 2299 * 64 + 1789 * 36   # 211 540
