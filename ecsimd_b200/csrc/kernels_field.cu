@@ -263,12 +263,45 @@ __global__ void __launch_bounds__(256) k_mix(uint32_t* __restrict__ out, const u
   out[tid] = t;
 }
 
+// Warp-specialised probe: even warps run only IMAD.WIDE chains, odd warps only IADD3 carry chains
+// (MODE 0), or every warp runs both interleaved (MODE 1), same total work per pair of warps.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_wspec(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool wwarp = ((threadIdx.x >> 7) & 1) == 0;  // warps 0-3 multiply, 4-7 add: one of each kind per sub-partition pair
+  uint32_t wl[8], wh[8], al[8], ah[8];
+  const uint32_t y = in[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { wl[j] = in[j] + tid; wh[j] = ~wl[j]; al[j] = wl[j] * 7u; ah[j] = wl[j] * 9u; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (MODE == 1 || wwarp) {
+#pragma unroll
+        for (int j = 0; j < (MODE == 1 ? 8 : 16); j++)
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(wl[j & 7]), "+r"(wh[j & 7]) : "r"(wh[(j + 3) & 7]), "r"(y));
+      }
+      if (MODE == 1 || !wwarp) {
+#pragma unroll
+        for (int j = 0; j < (MODE == 1 ? 12 : 24); j++)
+          asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(al[j & 7]), "+r"(ah[j & 7]) : "r"(ah[(j + 3) & 7]), "r"(al[(j + 5) & 7]));
+      }
+    }
+  }
+  uint32_t t = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) t += wl[j] ^ wh[j] ^ al[j] ^ ah[j];
+  out[tid] = t;
+}
+
 struct MixCombo { int nw, nl, nh, na; void (*fn)(uint32_t*, const uint32_t*, int); };
 #define MIX(a, b, c, d) {a, b, c, d, k_mix<a, b, c, d>}
 static const MixCombo g_mix[] = {
     MIX(8, 0, 0, 0), MIX(0, 8, 0, 0), MIX(0, 0, 8, 0), MIX(0, 8, 8, 0), MIX(0, 0, 0, 8), MIX(8, 0, 0, 4), MIX(8, 0, 0, 8),
     MIX(8, 0, 0, 12), MIX(0, 8, 8, 8), MIX(0, 8, 0, 8), MIX(0, 0, 8, 8), MIX(8, 8, 0, 0), MIX(8, 0, 8, 0), MIX(4, 8, 8, 8),
     MIX(8, 4, 0, 8), MIX(8, 0, 4, 8), MIX(4, 0, 0, 12), MIX(0, 12, 0, 0), MIX(0, 12, 0, 12),
+    {-1, 0, 0, 0, k_wspec<0>}, {-2, 0, 0, 0, k_wspec<1>},
     {0, 0, 0, 0, k_mix<0, 0, 0, 0, 8>}, {0, 0, 0, 8, k_mix<0, 0, 0, 8, 8>}, {0, 0, 0, 12, k_mix<0, 0, 0, 12, 8>}, {4, 0, 0, 8, k_mix<4, 0, 0, 8, 4>}};
 static const int g_nmix = (int)(sizeof(g_mix) / sizeof(g_mix[0]));
 
