@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libecb200.so")
+LIB_PATH = os.environ.get("ECB200_LIB", os.path.join(HERE, "libecb200.so"))  # override: A/B builds during development
 
 LAYOUT_LANE, LAYOUT_PACK4, LAYOUT_SOA = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0x00, 0x10
