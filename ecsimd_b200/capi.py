@@ -46,6 +46,9 @@ SYMBOLS = {
     "ecb200_scalar_mult_p256_1s": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_from_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
     "ecb200_to_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
+    "ecb200_convert_layout": (_i, [_vp, _u32, _vp, _u32, _i, _sz, _u32, _vp]),
+    "ecb200_bn_from_bytes_be": (_i, [_vp, _vp, _i, _sz, _u32, _vp]),
+    "ecb200_bn_to_bytes_be": (_i, [_vp, _vp, _i, _sz, _u32, _vp]),
     "ecb200_from_x": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_synth_values": (_i, [_vp, C.c_uint64, C.c_uint64, _i, _sz, _u32, _vp]),
     "ecb200_checksum": (_i, [_vp, _vp, _sz, _vp]),

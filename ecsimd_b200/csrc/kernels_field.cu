@@ -73,6 +73,35 @@ __global__ void __launch_bounds__(256) k_from_soa(void* __restrict__ dst, const 
   for (int c = 0; c < nc; c++) Layout<L>::store(dst, n, i, nc, c, Layout<L_SOA>::load(src, n, i, nc, c));
 }
 
+template <int LS, int LD>
+__global__ void __launch_bounds__(256) k_convert(void* __restrict__ dst, const void* __restrict__ src, size_t n, int nc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < nc; c++) Layout<LD>::store(dst, n, i, nc, c, Layout<LS>::load(src, n, i, nc, c));
+}
+
+// serialization.h:12-48 of the reference: a value <-> its 32-byte big-endian string.  `bytes` holds
+// n*nc strings back to back (lane-major, coordinate-minor: SEC1-style x|y for nc = 2).
+template <int L, bool TO_BYTES>
+__global__ void __launch_bounds__(256) k_bytes_be(void* __restrict__ vals, uint8_t* __restrict__ bytes, size_t n, int nc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < nc; c++) {
+    uint4* b = reinterpret_cast<uint4*>(bytes) + (i * nc + c) * 2;
+    if (TO_BYTES) {
+      const fe v = Layout<L>::load(vals, n, i, nc, c);
+      b[0] = make_uint4(__byte_perm(v.v[7], 0, 0x0123), __byte_perm(v.v[6], 0, 0x0123), __byte_perm(v.v[5], 0, 0x0123), __byte_perm(v.v[4], 0, 0x0123));
+      b[1] = make_uint4(__byte_perm(v.v[3], 0, 0x0123), __byte_perm(v.v[2], 0, 0x0123), __byte_perm(v.v[1], 0, 0x0123), __byte_perm(v.v[0], 0, 0x0123));
+    } else {
+      const uint4 hi = b[0], lo = b[1];
+      fe v;
+      v.v[7] = __byte_perm(hi.x, 0, 0x0123); v.v[6] = __byte_perm(hi.y, 0, 0x0123); v.v[5] = __byte_perm(hi.z, 0, 0x0123); v.v[4] = __byte_perm(hi.w, 0, 0x0123);
+      v.v[3] = __byte_perm(lo.x, 0, 0x0123); v.v[2] = __byte_perm(lo.y, 0, 0x0123); v.v[1] = __byte_perm(lo.z, 0, 0x0123); v.v[0] = __byte_perm(lo.w, 0, 0x0123);
+      Layout<L>::store(vals, n, i, nc, c, v);
+    }
+  }
+}
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   unsigned long long z = x + 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -385,6 +414,42 @@ int convert_from_soa(int L, void* dst, const void* src, size_t n, int nc, cudaSt
 
 using namespace ecb200;
 
+template <int LS>
+static int convert_dispatch(int LD, void* dst, const void* src, size_t n, int nc, cudaStream_t s) {
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (LD == L_LANE) k_convert<LS, L_LANE><<<blocks, 256, 0, s>>>(dst, src, n, nc);
+  else if (LD == L_PACK4) k_convert<LS, L_PACK4><<<blocks, 256, 0, s>>>(dst, src, n, nc);
+  else k_convert<LS, L_SOA><<<blocks, 256, 0, s>>>(dst, src, n, nc);
+  ECB_LAUNCH_CHECK();
+  return ECB200_OK;
+}
+
+template <bool TO_BYTES>
+static int bytes_call(void* vals, void* bytes, int ncoord, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (ncoord < 1 || ncoord > 3 || !vals || !bytes) { set_error("bad argument to ecb200_bn_*_bytes_be"); return ECB200_ERR_ARG; }
+  if (n == 0) return ECB200_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nb = operand_bytes(n, ncoord);
+  Scratch sc(s);
+  void *dv = vals, *db = bytes;
+  if (!on_device(flags)) {
+    if ((rc = sc.alloc(&dv, nb)) || (rc = sc.alloc(&db, nb))) return rc;
+    ECB_CUDA(cudaMemcpyAsync(TO_BYTES ? dv : db, TO_BYTES ? vals : bytes, nb, cudaMemcpyHostToDevice, s));
+  }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const int L = layout_of(flags);
+  if (L == L_LANE) k_bytes_be<L_LANE, TO_BYTES><<<blocks, 256, 0, s>>>(dv, (uint8_t*)db, n, ncoord);
+  else if (L == L_PACK4) k_bytes_be<L_PACK4, TO_BYTES><<<blocks, 256, 0, s>>>(dv, (uint8_t*)db, n, ncoord);
+  else k_bytes_be<L_SOA, TO_BYTES><<<blocks, 256, 0, s>>>(dv, (uint8_t*)db, n, ncoord);
+  ECB_LAUNCH_CHECK();
+  if (!on_device(flags)) {
+    ECB_CUDA(cudaMemcpyAsync(TO_BYTES ? bytes : vals, TO_BYTES ? db : dv, nb, cudaMemcpyDeviceToHost, s));
+    ECB_CUDA(cudaStreamSynchronize(s));
+  }
+  return ECB200_OK;
+}
 extern "C" {
 
 int ecb200_abi_version(void) { return ECB200_ABI_VERSION; }
@@ -548,6 +613,42 @@ int ecb200_microbench(int which, int blocks, int threads, int iters, double* ops
   const double per[7] = {64, 128, 120, 124, 64, 128, 184};  // counted in the SASS of each loop (tools/ + cuobjdump)
   *ops_per_iter = per[which];
   return ECB200_OK;
+}
+
+int ecb200_convert_layout(void* dst, uint32_t dst_layout, const void* src, uint32_t src_layout, int ncoord, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, src_layout | (flags & ~ECB200_LAYOUT_MASK));
+  if (!rc) rc = check_common(n, dst_layout | (flags & ~ECB200_LAYOUT_MASK));
+  if (rc) return rc;
+  if (ncoord < 1 || ncoord > 3 || !dst || !src) { set_error("bad argument to ecb200_convert_layout"); return ECB200_ERR_ARG; }
+  if (n == 0) return ECB200_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = operand_bytes(n, ncoord);
+  Scratch sc(s);
+  const void* dsrc = src;
+  void* ddst = dst;
+  if (!on_device(flags)) {
+    void *a, *b;
+    if ((rc = sc.alloc(&a, bytes)) || (rc = sc.alloc(&b, bytes))) return rc;
+    ECB_CUDA(cudaMemcpyAsync(a, src, bytes, cudaMemcpyHostToDevice, s));
+    dsrc = a; ddst = b;
+  }
+  const int LS = (int)(src_layout & ECB200_LAYOUT_MASK), LD = (int)(dst_layout & ECB200_LAYOUT_MASK);
+  if (LS == L_LANE) rc = convert_dispatch<L_LANE>(LD, ddst, dsrc, n, ncoord, s);
+  else if (LS == L_PACK4) rc = convert_dispatch<L_PACK4>(LD, ddst, dsrc, n, ncoord, s);
+  else rc = convert_dispatch<L_SOA>(LD, ddst, dsrc, n, ncoord, s);
+  if (rc) return rc;
+  if (!on_device(flags)) {
+    ECB_CUDA(cudaMemcpyAsync(dst, ddst, bytes, cudaMemcpyDeviceToHost, s));
+    ECB_CUDA(cudaStreamSynchronize(s));
+  }
+  return ECB200_OK;
+}
+
+int ecb200_bn_from_bytes_be(void* vals, const void* bytes, int ncoord, size_t n, uint32_t flags, void* stream) {
+  return bytes_call<false>(vals, const_cast<void*>(bytes), ncoord, n, flags, stream);
+}
+int ecb200_bn_to_bytes_be(void* bytes, const void* vals, int ncoord, size_t n, uint32_t flags, void* stream) {
+  return bytes_call<true>(const_cast<void*>(vals), bytes, ncoord, n, flags, stream);
 }
 
 int ecb200_microbench_mix(int combo, int blocks, int threads, int iters, int* counts4, float* ms, void* stream) {

@@ -147,6 +147,33 @@ def from_x(x, layout="lane", quirk=True):
     return y, ok
 
 
+def convert_layout(a, nc, src="lane", dst="soa"):
+    """re-lay n lanes x nc coordinates on the device (pack4 <-> soa <-> lane)"""
+    a = _in(a)
+    n = lanes_of(a, src, nc)
+    out = np.zeros(_shape(dst, n, nc), np.uint32)
+    capi.call("ecb200_convert_layout", capi._p(out), LAYOUTS[dst], capi._p(a), LAYOUTS[src], nc, n, MEM_HOST, None)
+    return out
+
+
+def bn_from_bytes_BE(b, nc=1, layout="lane"):
+    """serialization.h:12-23: (n, 32*nc) big-endian bytes -> values"""
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    n = b.size // (32 * nc)
+    out = np.zeros(_shape(layout, n, nc), np.uint32)
+    capi.call("ecb200_bn_from_bytes_be", capi._p(out), capi._p(b), nc, n, LAYOUTS[layout] | MEM_HOST, None)
+    return out
+
+
+def bn_to_bytes_BE(a, nc=1, layout="lane"):
+    """serialization.h:25-48: values -> (n, 32*nc) big-endian bytes"""
+    a = _in(a)
+    n = lanes_of(a, layout, nc)
+    out = np.zeros((n, 32 * nc), np.uint8)
+    capi.call("ecb200_bn_to_bytes_be", capi._p(out), capi._p(a), nc, n, LAYOUTS[layout] | MEM_HOST, None)
+    return out
+
+
 def synth_values(seed, start, n, kind, layout="lane"):
     out = np.zeros(_shape(layout, n, 1), np.uint32)
     capi.call("ecb200_synth_values", capi._p(out), seed, start, kind, n, LAYOUTS[layout] | MEM_HOST, None)

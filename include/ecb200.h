@@ -147,6 +147,16 @@ int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* st
  * reference's std::optional answers per 4-lane pack: a pack is valid iff all four ok bytes are 1. */
 int ecb200_from_x(void* y, uint8_t* ok, const void* x, size_t n, uint32_t flags, void* stream);
 
+/* ---- layout and byte-string adapters ----------------------------------------------------- */
+/* Re-lay a buffer of n lanes x ncoord coordinates (1 value, 2 affine, 3 Jacobian) from src_layout
+ * to dst_layout (ECB200_LAYOUT_*); `flags` carries only the memory space. */
+int ecb200_convert_layout(void* dst, uint32_t dst_layout, const void* src, uint32_t src_layout, int ncoord, size_t n, uint32_t flags, void* stream);
+/* bn_from_bytes_BE / bn_to_bytes_BE (include/ecsimd/serialization.h:12-48): `bytes` holds n*ncoord
+ * big-endian 32-byte strings back to back (lane-major; x|y for ncoord = 2, i.e. SEC1 uncompressed
+ * coordinates without the 0x04 prefix); `vals` is a value buffer in the layout given by `flags`. */
+int ecb200_bn_from_bytes_be(void* vals, const void* bytes, int ncoord, size_t n, uint32_t flags, void* stream);
+int ecb200_bn_to_bytes_be(void* bytes, const void* vals, int ncoord, size_t n, uint32_t flags, void* stream);
+
 /* ---- synthetic inputs, generated on the device (bench / large parity runs) ------ */
 /* value i = 4 x splitmix64 words of counter (seed * 0x100000001B3 + 4*(start+i) + limb);
  * kind 0: raw 256 bits (scalars); kind 1: canonical field element (minus p once if >= p). */

@@ -128,3 +128,20 @@ def test_full_size_properties(eng):
     o = _libs.oracle(8)
     idx = np.arange(0, n, 257)
     assert np.array_equal(ab[idx], o.mgry_mul(a[idx], b[idx]))
+
+
+def test_layout_and_byte_adapters(eng):
+    """pack4 <-> soa <-> lane on the device equals the numpy transposition; BE byte strings round-trip
+    and equal int.to_bytes (serialization.h:12-48 of the reference)"""
+    n = 1024
+    a = raw256(71, 3 * n).reshape(n, 24)
+    for src, dst in (("lane", "soa"), ("lane", "pack4"), ("pack4", "soa"), ("soa", "pack4"), ("soa", "lane"), ("pack4", "lane")):
+        conv = {"lane": lambda x: x, "soa": lambda x: eng.lane_to_soa(x, 3), "pack4": lambda x: eng.lane_to_pack4(x, 3)}
+        assert np.array_equal(eng.convert_layout(conv[src](a), 3, src, dst), conv[dst](a)), (src, dst)
+    v = raw256(72, 2 * n).reshape(n, 16)
+    b = eng.bn_to_bytes_BE(v, nc=2)
+    ints = _libs.to_ints(v.reshape(-1, 8))
+    want = np.frombuffer(b"".join(x.to_bytes(32, "big") for x in ints), np.uint8).reshape(n, 64)
+    assert np.array_equal(b, want)
+    assert np.array_equal(eng.bn_from_bytes_BE(b, nc=2), v)
+    assert np.array_equal(eng.soa_to_lane(eng.bn_from_bytes_BE(b, nc=2, layout="soa"), 2), v)
