@@ -75,23 +75,29 @@ __global__ void __launch_bounds__(128) k_point(void* out1, void* out2, const voi
 // lane unless k_bcast (scalar_mult_1s: one scalar for all lanes).  One block of 512 threads per SM
 // (16 warps, 128 registers each), all warps kept in step by a barrier per ladder iteration: the
 // ~52 KB loop body is then fetched once per SM instead of once per warp.
-template <bool QUIRK, int MODE, int THREADS>
+// L: layout of k, P and out -- the ladder reads 128 and writes 96 bytes per lane, so it takes the
+// caller's layout directly (no conversion pass, no extra kernels competing for the SMs).
+template <bool QUIRK, int MODE, int THREADS, int L>
 __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restrict__ out, const void* __restrict__ k,
                                                                  const void* __restrict__ P, size_t n, int k_bcast) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = i0 < n ? i0 : n - 1;  // surplus threads recompute the last lane (they must reach the barriers)
-  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : S::load(k, n, i, 1, 0);
+  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : Layout<L>::load(k, n, i, 1, 0);
   fe px, py;
   if (MODE == 0) {
-    px = S::load(P, n, i, 3, 0);
-    py = S::load(P, n, i, 3, 1);
+    px = Layout<L>::load(P, n, i, 3, 0);
+    py = Layout<L>::load(P, n, i, 3, 1);
   } else {
     const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
     px = fe_const(gx);
     py = fe_const(gy);
   }
   const jac r = pt_scalar_mult<QUIRK, true>(kk.v, px, py);
-  if (i0 < n) store_jac(out, n, i, r);
+  if (i0 < n) {
+    Layout<L>::store(out, n, i, 3, 0, r.x);
+    Layout<L>::store(out, n, i, 3, 1, r.y);
+    Layout<L>::store(out, n, i, 3, 2, r.z);
+  }
 }
 
 template <bool QUIRK>
@@ -236,17 +242,23 @@ static int point_call(void* out1, void* out2, const void* A, const void* B, size
 
 constexpr int kLadderThreads = 512;
 
-static int launch_ladder(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s) {
+// Layouts with a native ladder instance (bit-exact mode only: the NO_QUIRK variants exist for SOA).
+static bool ladder_has_layout(int L, bool q) { return L == L_SOA || q; }
+
+template <bool Q, int L>
+static int launch_ladder_ql(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
-  if (mode == 0) {
-    if (q) k_scalar_mult_sync<true, 0, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
-    else k_scalar_mult_sync<false, 0, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
-  } else {
-    if (q) k_scalar_mult_sync<true, 1, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
-    else k_scalar_mult_sync<false, 1, kLadderThreads><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
-  }
+  if (mode == 0) k_scalar_mult_sync<Q, 0, kLadderThreads, L><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+  else k_scalar_mult_sync<Q, 1, kLadderThreads, L><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
   ECB_LAUNCH_CHECK();
   return ECB200_OK;
+}
+static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s) {
+  if (L == L_SOA) return q ? launch_ladder_ql<true, L_SOA>(dout, dk, dP, mode, k_bcast, n, s) : launch_ladder_ql<false, L_SOA>(dout, dk, dP, mode, k_bcast, n, s);
+  if (L == L_LANE && q) return launch_ladder_ql<true, L_LANE>(dout, dk, dP, mode, k_bcast, n, s);
+  if (L == L_PACK4 && q) return launch_ladder_ql<true, L_PACK4>(dout, dk, dP, mode, k_bcast, n, s);
+  set_error("internal: no ladder instance for layout %d", L);
+  return ECB200_ERR_ARG;
 }
 
 // Host-memory batches are cut into chunks of two full waves (2 x 148 SMs x 512 lanes) that rotate
@@ -272,6 +284,7 @@ static int pipe_streams(cudaStream_t** out) {
 static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, cudaStream_t user) {
   const int L = layout_of(flags);
   const bool q = quirk_on(flags);
+  const bool native = ladder_has_layout(L, q);
   cudaStream_t* ss = nullptr;
   int rc = pipe_streams(&ss);
   if (rc) return rc;
@@ -281,20 +294,27 @@ static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, i
     const size_t m = (n - lo < kChunkLanes) ? n - lo : kChunkLanes;
     cudaStream_t s = ss[c % 3];
     Scratch sc(s);
-    void *rk, *rP = nullptr, *sk, *sP = nullptr, *so, *ro;
-    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&sk, operand_bytes(m, 1))) || (rc = sc.alloc(&so, operand_bytes(m, 3))) ||
-        (rc = sc.alloc(&ro, operand_bytes(m, 3))))
-      return rc;
+    void *rk, *rP = nullptr, *ro;
+    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&ro, operand_bytes(m, 3)))) return rc;
     // LANE and PACK4 are both contiguous per group of 4 lanes: a chunk is a byte range
     ECB_CUDA(cudaMemcpyAsync(rk, (const char*)k + lo * 32, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
-    if ((rc = convert_to_soa(L, sk, rk, m, 1, s))) return rc;
     if (mode == 0) {
-      if ((rc = sc.alloc(&rP, operand_bytes(m, 3))) || (rc = sc.alloc(&sP, operand_bytes(m, 3)))) return rc;
+      if ((rc = sc.alloc(&rP, operand_bytes(m, 3)))) return rc;
       ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
-      if ((rc = convert_to_soa(L, sP, rP, m, 3, s))) return rc;
     }
-    if ((rc = launch_ladder(so, sk, sP, mode, 0, m, q, s))) return rc;
-    if ((rc = convert_from_soa(L, ro, so, m, 3, s))) return rc;
+    if (native) {
+      if ((rc = launch_ladder(L, ro, rk, rP, mode, 0, m, q, s))) return rc;
+    } else {
+      void *sk, *sP = nullptr, *so;
+      if ((rc = sc.alloc(&sk, operand_bytes(m, 1))) || (rc = sc.alloc(&so, operand_bytes(m, 3)))) return rc;
+      if ((rc = convert_to_soa(L, sk, rk, m, 1, s))) return rc;
+      if (mode == 0) {
+        if ((rc = sc.alloc(&sP, operand_bytes(m, 3)))) return rc;
+        if ((rc = convert_to_soa(L, sP, rP, m, 3, s))) return rc;
+      }
+      if ((rc = launch_ladder(L_SOA, so, sk, sP, mode, 0, m, q, s))) return rc;
+      if ((rc = convert_from_soa(L, ro, so, m, 3, s))) return rc;
+    }
     ECB_CUDA(cudaMemcpyAsync((char*)out + lo * 96, ro, operand_bytes(m, 3), cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < 3; i++) ECB_CUDA(cudaStreamSynchronize(ss[i]));
@@ -311,7 +331,11 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   }
   if (!on_device(flags) && layout_of(flags) != L_SOA && !k_bcast && n > kChunkLanes)
     return scalar_mult_host_pipelined(out, k, P, mode, n, flags, (cudaStream_t)stream);
-  Staged st((cudaStream_t)stream, flags, n);
+  const int L = layout_of(flags);
+  const bool q = quirk_on(flags);
+  // native layout: the kernel reads/writes the caller's layout (only the memory space is staged)
+  const bool native = ladder_has_layout(L, q);
+  Staged st((cudaStream_t)stream, native ? ((flags & ~ECB200_LAYOUT_MASK) | ECB200_LAYOUT_SOA) : flags, n);  // SOA = "no conversion" for Staged
   const void *dk = nullptr, *dP = nullptr;
   void* dout = nullptr;
   if (k_bcast) {
@@ -322,7 +346,7 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   } else if ((rc = st.in(k, 1, &dk))) return rc;
   if (mode == 0 && (rc = st.in(P, 3, &dP))) return rc;
   if ((rc = st.out(out, 3, &dout))) return rc;
-  if ((rc = launch_ladder(dout, dk, dP, mode, k_bcast, n, quirk_on(flags), st.s))) return rc;
+  if ((rc = launch_ladder(native ? L : L_SOA, dout, dk, dP, mode, k_bcast, n, q, st.s))) return rc;
   return st.finish();
 }
 
