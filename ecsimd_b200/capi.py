@@ -46,6 +46,17 @@ SYMBOLS = {
     "ecb200_scalar_mult_p256_1s": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_from_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
     "ecb200_to_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mod_add": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mod_sub": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mod_shift_left_one": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mgry_mul": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mgry_sqr": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_from_classical": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_to_classical": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_mgry_pow": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_gen_opposite": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_mul512": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
+    "ecb200_square512": (_i, [_vp, _vp, _sz, _u32, _vp]),
     "ecb200_convert_layout": (_i, [_vp, _u32, _vp, _u32, _i, _sz, _u32, _vp]),
     "ecb200_bn_from_bytes_be": (_i, [_vp, _vp, _i, _sz, _u32, _vp]),
     "ecb200_bn_to_bytes_be": (_i, [_vp, _vp, _i, _sz, _u32, _vp]),

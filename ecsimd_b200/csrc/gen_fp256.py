@@ -429,6 +429,22 @@ def gen_mul():
     return g
 
 
+def gen_mul512():
+    """product + merge only: T = a*b as 16 words t0..t15 (used by the generic-prime path)"""
+    g = Emit()
+    touched = emit_products(g, MUL_E_CHAINS, MUL_O_CHAINS, "a%d", "b%d", {"e": 14, "o": None})
+    g.begin()
+    g.add32("t0", "e0", 0, False, False)
+    g.end()
+    g.begin()
+    for w in range(1, 16):
+        ev = "e%d" % w if "e%d" % w in touched else 0
+        ov = "o%d" % w if "o%d" % w in touched else 0
+        g.add32("t%d" % w, ev, ov, w > 1, w < 15)
+    g.end()
+    return g
+
+
 def gen_sqr():
     _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
     g = Emit()
@@ -523,14 +539,15 @@ namespace ecb200 {
 """
 
 
-def _emit_fn(name, g, nin):
+def _emit_fn(name, g, nin, outs=None):
     regs = set()
     for s in g.stmts:
         regs.update(s["rw"]); regs.update(s["wo"]); regs.update(s["ro"])
-    params = ["h%d" % k for k in range(9)] + ["a%d" % k for k in range(8)] + (["b%d" % k for k in range(8)] if nin == 2 else [])
+    outs = outs or ["h%d" % k for k in range(9)]
+    params = outs + ["a%d" % k for k in range(8)] + (["b%d" % k for k in range(8)] if nin == 2 else [])
     local = sorted(regs - set(params), key=lambda x: (x.rstrip("0123456789"), int("0" + "".join(ch for ch in x if ch.isdigit()))))
     txt = "__device__ __forceinline__ void %s(\n" % name
-    txt += "    " + ", ".join("uint32_t& h%d" % k for k in range(9)) + ",\n"
+    txt += "    " + ", ".join("uint32_t& %s" % o for o in outs) + ",\n"
     txt += "    " + ", ".join("uint32_t a%d" % k for k in range(8))
     if nin == 2:
         txt += ",\n    " + ", ".join("uint32_t b%d" % k for k in range(8))
@@ -544,7 +561,18 @@ def emit_header(path):
     gm, gs = gen_mul(), gen_sqr()
     nm = check(gm, unary=False)
     ns = check(gs, unary=True)
-    txt = HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1) + "}  // namespace ecb200\n"
+    g5 = gen_mul512()
+    rnd = random.Random(5)
+    for x, y in _cases(500, 5, False):
+        env = {}
+        for k in range(8):
+            env["a%d" % k] = (x >> (32 * k)) & M32
+            env["b%d" % k] = (y >> (32 * k)) & M32
+        simulate(g5.ir, env)
+        assert sum(env["t%d" % k] << (32 * k) for k in range(16)) == x * y
+    txt = (HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1) +
+           "// T = a*b, the exact 512-bit product (mul.h:150-158), 16 words\n" +
+           _emit_fn("fp_mul512_words", g5, 2, outs=["t%d" % k for k in range(16)]) + "}  // namespace ecb200\n")
     with open(path, "w") as f:
         f.write(txt)
     return nm + ns, gm, gs

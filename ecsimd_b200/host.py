@@ -147,6 +147,55 @@ def from_x(x, layout="lane", quirk=True):
     return y, ok
 
 
+class GenericField:
+    """the field layer for a run-time modulus (reference: templates over P; its tests use secp256k1)"""
+
+    def __init__(self, p_int):
+        self.p = np.array([(p_int >> (32 * i)) & 0xFFFFFFFF for i in range(8)], np.uint32)
+
+    def _u(self, name, a, extra=(), quirk=True, wout=8):
+        a = _in(a)
+        n = a.shape[0]
+        out = np.zeros((n, wout), np.uint32)
+        capi.call(name, capi._p(out), capi._p(a), *extra, capi._p(self.p), n, _flags("lane", quirk), None)
+        return out
+
+    def _b(self, name, a, b):
+        a, b = _in(a), _in(b)
+        out = np.zeros_like(a)
+        capi.call(name, capi._p(out), capi._p(a), capi._p(b), capi._p(self.p), a.shape[0], _flags("lane", True), None)
+        return out
+
+    def mod_add(self, a, b): return self._b("ecb200_gen_mod_add", a, b)
+    def mod_sub(self, a, b): return self._b("ecb200_gen_mod_sub", a, b)
+    def mgry_mul(self, a, b): return self._b("ecb200_gen_mgry_mul", a, b)
+    def mod_shift_left_one(self, a): return self._u("ecb200_gen_mod_shift_left_one", a)
+    def mgry_sqr(self, a, quirk=True): return self._u("ecb200_gen_mgry_sqr", a, quirk=quirk)
+    def from_classical(self, a): return self._u("ecb200_gen_from_classical", a)
+    def to_classical(self, a): return self._u("ecb200_gen_to_classical", a)
+    def opposite(self, a): return self._u("ecb200_gen_opposite", a)
+
+    def mgry_pow(self, a, e_int, quirk=True):
+        e = np.array([(e_int >> (32 * i)) & 0xFFFFFFFF for i in range(8)], np.uint32)
+        return self._u("ecb200_gen_mgry_pow", a, extra=(capi._p(e),), quirk=quirk)
+
+
+def mul512(a, b):
+    """mul(a, b): exact 512-bit product, (n, 16) words  (mul.h:150-158)"""
+    a, b = _in(a), _in(b)
+    out = np.zeros((a.shape[0], 16), np.uint32)
+    capi.call("ecb200_mul512", capi._p(out), capi._p(a), capi._p(b), a.shape[0], _flags("lane", True), None)
+    return out
+
+
+def square512(a):
+    """square(a) of the reference, with its lost carry (mul.h:214-221)"""
+    a = _in(a)
+    out = np.zeros((a.shape[0], 16), np.uint32)
+    capi.call("ecb200_square512", capi._p(out), capi._p(a), a.shape[0], _flags("lane", True), None)
+    return out
+
+
 def convert_layout(a, nc, src="lane", dst="soa"):
     """re-lay n lanes x nc coordinates on the device (pack4 <-> soa <-> lane)"""
     a = _in(a)

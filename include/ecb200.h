@@ -147,6 +147,26 @@ int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* st
  * reference's std::optional answers per 4-lane pack: a pack is valid iff all four ok bytes are 1. */
 int ecb200_from_x(void* y, uint8_t* ok, const void* x, size_t n, uint32_t flags, void* stream);
 
+/* ---- the field layer for a modulus given at run time -------------------------------------------
+ * The reference's field templates take the prime as a parameter, and its own field tests use the
+ * secp256k1 prime (tests/mgry.cpp:25-27, tests/ops.cpp:221-252).  p8: the modulus as 8 x u32 in HOST
+ * memory, least-significant word first; it must be odd with bit 255 set (R = 2^256).  Same value
+ * semantics as the templates for any 256-bit input, including the squaring defect. */
+int ecb200_gen_mod_add(void* out, const void* a, const void* b, const uint32_t* p8, size_t n, uint32_t flags, void* stream);          /* modular.h:10-15 */
+int ecb200_gen_mod_sub(void* out, const void* a, const void* b, const uint32_t* p8, size_t n, uint32_t flags, void* stream);          /* modular.h:24-41 */
+int ecb200_gen_mod_shift_left_one(void* out, const void* a, const uint32_t* p8, size_t n, uint32_t flags, void* stream);              /* modular.h:17-22 */
+int ecb200_gen_mgry_mul(void* out, const void* a, const void* b, const uint32_t* p8, size_t n, uint32_t flags, void* stream);         /* mgry_ops.h:31-35 */
+int ecb200_gen_mgry_sqr(void* out, const void* a, const uint32_t* p8, size_t n, uint32_t flags, void* stream);                        /* mgry_ops.h:37-42 */
+int ecb200_gen_from_classical(void* out, const void* a, const uint32_t* p8, size_t n, uint32_t flags, void* stream);                  /* mgry.h:47-50 */
+int ecb200_gen_to_classical(void* out, const void* a, const uint32_t* p8, size_t n, uint32_t flags, void* stream);                    /* mgry.h:52-55 */
+/* out = mgry_pow(a, e): e8 = exponent, 8 x u32 in HOST memory (inverse: p-2, sqrt: (p+1)/4)   mgry_ops.h:44-86 */
+int ecb200_gen_mgry_pow(void* out, const void* a, const uint32_t* e8, const uint32_t* p8, size_t n, uint32_t flags, void* stream);
+int ecb200_gen_opposite(void* out, const void* a, const uint32_t* p8, size_t n, uint32_t flags, void* stream);                        /* gfp.h:60-64 */
+/* out16 = mul(a,b): the exact 256x256 -> 512-bit product (mul.h:150-158), and square(a) with the
+ * reference's lost carry (mul.h:214-221); ECB200_LAYOUT_LANE only, 16 x u32 per lane out. */
+int ecb200_mul512(void* out16, const void* a, const void* b, size_t n, uint32_t flags, void* stream);
+int ecb200_square512(void* out16, const void* a, size_t n, uint32_t flags, void* stream);
+
 /* ---- layout and byte-string adapters ----------------------------------------------------- */
 /* Re-lay a buffer of n lanes x ncoord coordinates (1 value, 2 affine, 3 Jacobian) from src_layout
  * to dst_layout (ECB200_LAYOUT_*); `flags` carries only the memory space. */

@@ -492,6 +492,97 @@ void orc_from_affine(u32* outJ, const u32* xy, size_t n, int nt) { RUN(r_fa, out
 void orc_to_affine(u32* xy, const u32* J, size_t n, int nt) { RUN(r_ta, xy, 0, J, 0, 0); }
 void orc_from_x(u32* y, uint8_t* ok, const u32* x, size_t n, int nt) { RUN(r_fx, y, 0, x, 0, ok); }
 
+/* ---- the same field layer for a modulus given at run time ---------------------------------------
+ * (the reference's templates take the prime as a parameter; its field tests use secp256k1:
+ * tests/mgry.cpp:25-27, tests/ops.cpp:221-252).  p: 8 words, odd, bit 255 set. */
+typedef struct { u32 p[8], r1[8], rr[8], mprime; } genp;
+static u32 geq8(const u32* a, const u32* p) { for (int i = 7; i >= 0; i--) if (a[i] != p[i]) return a[i] > p[i]; return 1; }
+static void gen_setup(genp* g, const u32* p) {
+  memcpy(g->p, p, 32);
+  u32 inv = p[0];
+  for (int i = 0; i < 5; i++) inv *= 2u - p[0] * inv;
+  g->mprime = 0u - inv;                                   /* mgry_mul.h:33-40 */
+  u32 x[8] = {1, 0, 0, 0, 0, 0, 0, 0}, d[8];
+  for (int i = 0; i < 512; i++) {                          /* R mod p, R^2 mod p: mgry_csts.h:20-21 */
+    u32 c = x[7] >> 31;
+    for (int k = 7; k > 0; k--) x[k] = (x[k] << 1) | (x[k - 1] >> 31);
+    x[0] <<= 1;
+    if (c || geq8(x, p)) { sub8(d, x, p); memcpy(x, d, 32); }
+    if (i == 255) memcpy(g->r1, x, 32);
+  }
+  memcpy(g->rr, x, 32);
+}
+static void g_reduce_once(u32 r[8], const u32 s[8], u32 c, const genp* g) {  /* sub.h:46-69 */
+  u32 d[8];
+  u32 bw = sub8(d, s, g->p);
+  memcpy(r, (bw && !c) ? s : d, 32);
+}
+static void g_add(u32 r[8], const u32 a[8], const u32 b[8], const genp* g) { u32 s[8]; u32 c = add8(s, a, b); g_reduce_once(r, s, c, g); }
+static void g_sub(u32 r[8], const u32 a[8], const u32 b[8], const genp* g) {
+  u32 d[8], da[8];
+  u32 bw = sub8(d, a, b);
+  add8(da, d, g->p);
+  memcpy(r, bw ? da : d, 32);
+}
+static void g_shl1(u32 r[8], const u32 a[8], const genp* g) {
+  u32 s[8];
+  u32 c = a[7] >> 31;
+  for (int i = 7; i > 0; i--) s[i] = (a[i] << 1) | (a[i - 1] >> 31);
+  s[0] = a[0] << 1;
+  g_reduce_once(r, s, c, g);
+}
+static void g_redc(u32 r[8], const u32 t[16], const genp* g) {  /* mgry_mul.h:84-121, generic digits of p */
+  u64 acc[17];
+  for (int k = 0; k < 16; k++) acc[k] = t[k];
+  acc[16] = 0;
+  for (int i = 0; i < 8; i++) {
+    u32 m = (u32)acc[i] * g->mprime;
+    u64 carry = 0;
+    for (int k = 0; k < 8; k++) { u64 x = acc[i + k] + (u64)m * g->p[k] + carry; acc[i + k] = x & M32; carry = x >> 32; }
+    for (int k = i + 8; k < 17; k++) { u64 x = acc[k] + carry; acc[k] = x & M32; carry = x >> 32; }
+  }
+  u32 s[8];
+  for (int k = 0; k < 8; k++) s[k] = (u32)acc[8 + k];
+  g_reduce_once(r, s, (u32)acc[16], g);
+}
+static void g_mul(u32 r[8], const u32 a[8], const u32 b[8], const genp* g) { u32 t[16]; orc1_mul512(t, a, b); g_redc(r, t, g); }
+static void g_sqr(u32 r[8], const u32 a[8], const genp* g) { u32 t[16]; square512_impl(t, a); g_redc(r, t, g); }
+static void g_pow(u32 r[8], const u32 a[8], const u32 e[8], const genp* g) {  /* mgry_ops.h:44-86 */
+  int top = -1;
+  for (int b = 255; b >= 0; b--) if ((e[b >> 5] >> (b & 31)) & 1) { top = b; break; }
+  u32 res[8], base[8], t[8];
+  memcpy(res, g->r1, 32);
+  memcpy(base, a, 32);
+  for (int b = 0; b <= top; b++) {
+    if ((e[b >> 5] >> (b & 31)) & 1) { g_mul(t, res, base, g); memcpy(res, t, 32); }
+    if (b < top) { g_sqr(t, base, g); memcpy(base, t, 32); }
+  }
+  memcpy(r, res, 32);
+}
+/* op: 0 mod_add 1 mod_sub 2 mod_shift_left_one 3 mgry_mul 4 mgry_sqr 5 from_classical 6 to_classical
+ *     7 mgry_pow (e) 8 opposite */
+void orc_gen_op(int op, u32* o, const u32* a, const u32* b, const u32* e, const u32* p, size_t n) {
+  genp g;
+  gen_setup(&g, p);
+  u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0}, pm1r[8], t[8];
+  sub8(pm1r, g.p, g.r1);                                   /* (p-1)R mod p = p - (R mod p) */
+  for (size_t i = 0; i < n; i++) {
+    const u32 *x = a + 8 * i, *y = b ? b + 8 * i : NULL;
+    u32* r = o + 8 * i;
+    switch (op) {
+      case 0: g_add(r, x, y, &g); break;
+      case 1: g_sub(r, x, y, &g); break;
+      case 2: g_shl1(r, x, &g); break;
+      case 3: g_mul(r, x, y, &g); break;
+      case 4: g_sqr(r, x, &g); break;
+      case 5: g_mul(r, x, g.rr, &g); break;
+      case 6: g_mul(r, x, one, &g); break;
+      case 7: g_pow(r, x, e, &g); break;
+      default: g_sub(t, x, g.r1, &g); g_sub(r, pm1r, t, &g); break;   /* gfp.h:60-64 */
+    }
+  }
+}
+
 void orc_constants(u32* out) {
   memcpy(out, P256, 32); memcpy(out + 8, R_P, 32); memcpy(out + 16, RSQ_P, 32); memcpy(out + 24, PM1_R_P, 32);
   memcpy(out + 32, AM, 32); memcpy(out + 40, BM, 32);

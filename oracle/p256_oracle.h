@@ -54,6 +54,9 @@ void orc_to_affine(uint32_t* xy, const uint32_t* J, size_t n, int nt);
 /* y = sqrt(x^3-3x+b) per lane; ok[i] = 1 iff lane i is a square (the reference
  * answers per 4-lane pack: a pack is valid iff all 4 of its lanes are) */
 void orc_from_x(uint32_t* y, uint8_t* ok, const uint32_t* x, size_t n, int nt);
+/* run-time modulus p (8 words, odd, bit 255 set); op: 0 mod_add 1 mod_sub 2 mod_shift_left_one
+ * 3 mgry_mul 4 mgry_sqr 5 from_classical 6 to_classical 7 mgry_pow(e) 8 opposite */
+void orc_gen_op(int op, uint32_t* o, const uint32_t* a, const uint32_t* b, const uint32_t* e, const uint32_t* p, size_t n);
 void orc_constants(uint32_t* out /* 64 x u32: P, R, R^2, (p-1)R, Am, Bm, Gx_m, Gy_m */);
 
 /* instrumentation: counts of field ops executed by the calling thread since

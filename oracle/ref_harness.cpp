@@ -211,6 +211,38 @@ void ref_from_x(uint64_t* y, uint8_t* ok4, const uint64_t* x, size_t n) {
     if (r) store4(y, 4, i, n, r->y());
   }
 }
+// ---- the reference's field layer on the secp256k1 prime, as in its own tests (tests/mgry.cpp:25-27,
+// tests/ops.cpp:221-252).  op codes as in orc_gen_op.
+namespace {
+struct PK1 {
+  static constexpr auto value = bn_from_bytes_BE<bignum_256>("FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEFFFFFC2F"_hex);
+};
+using WMBNK = wide_mgry_bignum<WBN, PK1>;
+using GFPK = GFp<WBN, PK1>;
+}  // namespace
+void ref_k1_op(int op, uint64_t* o, const uint64_t* a, const uint64_t* b, const uint64_t* e, size_t n) {
+  const WBN p{PK1::value};
+  BN ee{};
+  if (e) std::memcpy(&ee, e, 32);
+  for (size_t i = 0; i < n; i += 4) {
+    const WBN x = load4(a, 4, i, n);
+    const WBN y = b ? load4(b, 4, i, n) : x;
+    WBN r;
+    switch (op) {
+      case 0: r = mod_add(x, y, p); break;
+      case 1: r = mod_sub(x, y, p); break;
+      case 2: r = mod_shift_left_one(x, p); break;
+      case 3: r = mgry_mul(WMBNK{x}, WMBNK{y}).wbn(); break;
+      case 4: r = mgry_sqr(WMBNK{x}).wbn(); break;
+      case 5: r = WMBNK::from_classical(x).wbn(); break;
+      case 6: r = WMBNK{x}.to_classical(); break;
+      case 7: r = mgry_pow(WMBNK{x}, ee).wbn(); break;
+      default: r = GFPK{WMBNK{x}}.opposite().wbn(); break;
+    }
+    store4(o, 4, i, n, r);
+  }
+}
+
 // constants, for cross-checking the literals baked into the CUDA / C code
 void ref_constants(uint64_t* out /* 32 x u64: P, R, R^2, (p-1)R, Am, Bm, Gx_m, Gy_m */) {
   auto put = [&](int idx, BN const& b) { std::memcpy(out + 4 * idx, &b, 32); };
