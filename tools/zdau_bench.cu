@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_zdau_skew2(uint32_t* io, int ite
     for (int i = 0; i < 8; i++) io[t * 40 + c * 8 + i] = v[c].v[i];
 }
 
+#ifndef BENCH_UNROLL
+#define BENCH_UNROLL 1
+#endif
 template <bool CALLS, bool SYNC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_zdau(uint32_t* io, int iters) {
   const size_t t = (size_t)threadIdx.x + (size_t)blockIdx.x * blockDim.x;
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_zdau(uint32_t* io, int iters)
   Lazy md;
   for (int c = 0; c < 5; c++)
     for (int i = 0; i < 8; i++) v[c].v[i] = io[t * 40 + c * 8 + i];
-#pragma unroll 1
+  constexpr int kUnroll = BENCH_UNROLL;
+#pragma unroll kUnroll
   for (int it = 0; it < iters; it++) {
     const uint32_t sw = (v[0].v[0] >> (it & 31)) & 1u;  // data-dependent swap like the ladder
     fe_cswap(sw, v[0], v[2]);
@@ -128,9 +132,12 @@ int main(int argc, char** argv) {
   cudaMalloc(&d, h.size() * 4);
   cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
   run("inline_128x3", k_zdau<false, false, 128, 3>, 128, 3, d, iters);
+  run("inline_128x4", k_zdau<false, false, 128, 4>, 128, 4, d, iters);
+  run("inline_nosync_512x1", k_zdau<false, false, 512, 1>, 512, 1, d, iters);
   run("inline_sync_384x1", k_zdau<false, true, 384, 1>, 384, 1, d, iters);
   run("skew2_512x1", k_zdau_skew2<512>, 512, 1, d, iters);
   run("inline_sync_512x1", k_zdau<false, true, 512, 1>, 512, 1, d, iters);
+  run("inline_sync_256x2", k_zdau<false, true, 256, 2>, 256, 2, d, iters);
 
 #if VARIANT_CALLS
   run("calls_128x3", k_zdau<true, false, 128, 3>, 128, 3, d, iters);
