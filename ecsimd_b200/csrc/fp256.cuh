@@ -234,13 +234,37 @@ static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t
   return (uint32_t)m == 0x7fffffffu;
 }
 
-// First-level filter on the FMA pipe's cheap 32-bit IMAD (2 clk/warp against 5 for IMAD.HI):
-// with A = a_i >> 16, B = a_j >> 16 we have A*B*2^32 <= a_i*a_j < (A*B + A + B + 1)*2^32, so
-// hi32(a_i*a_j) == 0x7fffffff forces A*B into [0x7ffe0000, 0x7fffffff], i.e.
-// (A*B + 0x80020000) mod 2^32 < 0x20000.  An unsigned 3-input min over the 28 products keeps it
-// to one IMAD + half a VIMNMX3 per cross product.  False-positive rate ~ 28 * 2^-15 per lane,
-// resolved by the exact test above; real hits (~6.5e-9 per lane) take the slow path.
-__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a) {
+// First-level filter.  Eight of the 28 cross products (ECB200_SQR_EXACT_PAIRS: every a_0*a_j and
+// a_1*a_7) are the first to land on their accumulator pair in fp_sqr_t9, so their exact high words
+// are there for free: qx = signed max of them, INT_MAX <=> hit.  The other 20 get a necessary
+// condition on the cheap 32-bit IMAD (2 clk/warp against 5 for IMAD.HI): with A = a_i >> 16,
+// B = a_j >> 16 we have A*B*2^32 <= a_i*a_j < (A*B + A + B + 1)*2^32, so hi32(a_i*a_j) == 0x7fffffff
+// forces A*B into [0x7ffe0000, 0x7fffffff], i.e. (A*B + 0x80020000) mod 2^32 < 0x20000.  An
+// unsigned 3-input min keeps it to one IMAD + half a VIMNMX3 per product.  The result m is
+// "< 0x20000 <=> maybe"; false-positive rate ~ 28 * 2^-15 per lane, resolved by the exact test
+// above; real hits (~6.5e-9 per lane) take the slow path.  `m` chains through several squarings.
+__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a, uint32_t qx, uint32_t m = 0xffffffffu) {
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 1; i < 8; i++) h[i] = a.v[i] >> 16;
+  // 0x7fffffff - qx: 0 on an exact hit, >= 0x80000000 when qx is "negative", small only near INT_MAX
+  uint32_t pend = 0x7fffffffu - qx;
+  bool have = true;
+#pragma unroll
+  for (int i = 1; i < 7; i++) {
+#pragma unroll
+    for (int j = i + 1; j < 8; j++) {
+      if (i == 1 && j == 7) continue;  // in qx
+      const uint32_t y = h[i] * h[j] + 0x80020000u;
+      if (have) { m = __vimin3_u32(m, pend, y); have = false; }
+      else { pend = y; have = true; }
+    }
+  }
+  if (have) m = min(m, pend);
+  return m;
+}
+// all 28 pairs through the IMAD condition (callers that do not run fp_sqr_t9: the generic-prime path)
+__device__ __forceinline__ uint32_t fp_sqr_quirk_filter_all(const fe& a) {
   uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) h[i] = a.v[i] >> 16;
@@ -256,21 +280,23 @@ __device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a) {
   }
   return m;
 }
+static_assert(sizeof((const int[][2])ECB200_SQR_EXACT_PAIRS) == 8 * 2 * sizeof(int), "fp_sqr_quirk_filter assumes the 8 exact pairs (0,j), (1,7)");
 
 template <bool QUIRK, class M>
-__device__ __forceinline__ fe fp_sqr_core(const fe& a, M& mode) {
+__device__ __forceinline__ fe fp_sqr_core(const fe& a, M& mode, uint32_t& qx) {
   fe t;
   uint32_t t8;
-  fp_sqr_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8,
+  fp_sqr_t9(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t8, qx,
             a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7]);
   return fp_reduce_once(t, t8, mode);
 }
 
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
-  fe r = fp_sqr_core<QUIRK>(a, mode);
+  uint32_t qx;
+  fe r = fp_sqr_core<QUIRK>(a, mode, qx);
   if (QUIRK) {
-    if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
+    if (__builtin_expect(fp_sqr_quirk_filter(a, qx) < 0x20000u, 0)) {
       uint32_t in[8], out[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
@@ -285,9 +311,10 @@ __device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
 }
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr(const fe& a, Lazy& mode) {
-  const fe r = fp_sqr_core<QUIRK>(a, mode);
+  uint32_t qx;
+  const fe r = fp_sqr_core<QUIRK>(a, mode, qx);
   if (QUIRK) {
-    if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
+    if (__builtin_expect(fp_sqr_quirk_filter(a, qx) < 0x20000u, 0)) {
       uint32_t in[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
@@ -298,6 +325,50 @@ __device__ __forceinline__ fe fp_sqr(const fe& a, Lazy& mode) {
 }
 template <bool QUIRK = true>
 __device__ __forceinline__ fe fp_sqr(const fe& a) { Exact e; return fp_sqr<QUIRK>(a, e); }
+
+// Grouped form for the point formulas: fp_sqr_acc squares and only folds the first-level filter of
+// its operand into `fm`; fp_quirk_check then resolves a whole group of squarings with ONE branch.
+// Exact mode resolves each squaring in place (fm unused), so both modes share the formulas.
+template <bool QUIRK>
+__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Exact& mode, uint32_t&) { return fp_sqr<QUIRK>(a, mode); }
+template <bool QUIRK>
+__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Lazy& mode, uint32_t& fm) {
+  uint32_t qx;
+  const fe r = fp_sqr_core<QUIRK>(a, mode, qx);
+  if (QUIRK) fm = fp_sqr_quirk_filter(a, qx, fm);
+  return r;
+}
+static __device__ __noinline__ uint32_t fp_quirk_exact3(const uint32_t* a, int n) {
+  uint32_t hit = 0;
+  for (int k = 0; k < n; k++) hit |= fp_sqr_quirk_filter_exact(a + 8 * k);
+  return hit;
+}
+template <bool QUIRK>
+__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, const fe&) {}
+template <bool QUIRK>
+__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, const fe&, const fe&) {}
+template <bool QUIRK>
+__device__ __forceinline__ void fp_quirk_check(Lazy& mode, uint32_t fm, const fe& a, const fe& b) {
+  if (QUIRK) {
+    if (__builtin_expect(fm < 0x20000u, 0)) {
+      uint32_t in[16];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; }
+      if (fp_quirk_exact3(in, 2)) mode.dirty = 1u;
+    }
+  }
+}
+template <bool QUIRK>
+__device__ __forceinline__ void fp_quirk_check(Lazy& mode, uint32_t fm, const fe& a, const fe& b, const fe& c) {
+  if (QUIRK) {
+    if (__builtin_expect(fm < 0x20000u, 0)) {
+      uint32_t in[24];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; in[16 + i] = c.v[i]; }
+      if (fp_quirk_exact3(in, 3)) mode.dirty = 1u;
+    }
+  }
+}
 
 // gfp.h:60-64: opposite(a) = (p-1)R - (a - R)
 __device__ __forceinline__ fe fp_neg(const fe& a) { return fp_sub(fe_PM1R(), fp_sub(a, fe_R())); }

@@ -139,7 +139,7 @@ __device__ __forceinline__ fe gen_sqr(const fe& a, const GenPrime& P) {
                   a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
                   a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7]);
   if (QUIRK) {
-    if (__builtin_expect(fp_sqr_quirk_filter(a) < 0x20000u, 0)) {
+    if (__builtin_expect(fp_sqr_quirk_filter_all(a) < 0x20000u, 0)) {
       uint32_t in[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];

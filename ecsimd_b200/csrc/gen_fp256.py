@@ -56,6 +56,12 @@ class Emit:
         self.ir.append(("endchain",))
         self.cur = None
 
+    def raw(self, text, ir, regs=()):
+        """a plain C++ statement between two asm statements (modelled by the IR tuple `ir`)"""
+        assert self.cur is None
+        self.stmts.append({"raw": text, "lines": [], "rw": [], "ro": [], "wo": list(regs)})
+        self.ir.append(ir)
+
     def _reg(self, name, mode):
         c = self.cur
         if isinstance(name, int):
@@ -85,8 +91,9 @@ class Emit:
     # --- IR ops ----------------------------------------------------------------
     def mulw(self, lo, hi, x, y):
         """(hi:lo) = x*y   -- fresh pair, no carries"""
-        self.line("mul.lo.u32 {0}, {1}, {2};", (lo, "w"), (x, "r"), (y, "r"))
-        self.line("mul.hi.u32 {0}, {1}, {2};", (hi, "w"), (x, "r"), (y, "r"))
+        # one 64-bit multiply, so that ptxas cannot split it into IMAD + IMAD.HI (5 clk) when the two
+        # halves have different consumers
+        self.line("{{ .reg .b64 w; mul.wide.u32 w, {2}, {3}; mov.b64 {{{0}, {1}}}, w; }}", (lo, "w"), (hi, "w"), (x, "r"), (y, "r"))
         self.ir.append(("mulw", lo, hi, x, y))
 
     def madw(self, lo, hi, x, y, cin, cout, fresh=(False, False)):
@@ -156,6 +163,9 @@ class Emit:
     def cxx(self, indent="  "):
         out = []
         for s in self.stmts:
+            if "raw" in s:
+                out.append(indent + s["raw"])
+                continue
             names = s["rw"] + s["wo"] + s["ro"]
             idx = {n: i for i, n in enumerate(names)}
             body = []
@@ -244,6 +254,12 @@ def simulate(ir, env):
         elif k == "setb":
             assert val(ins[1]) in (0, M32)
             cc = 1 if val(ins[1]) else 0
+        elif k == "copy":
+            env[ins[1]] = val(ins[2])
+        elif k == "max3s":
+            def sgn(v):
+                return v - 2**32 if v >= 2**31 else v
+            env[ins[1]] = max(sgn(val(x)) for x in ins[2:]) & M32
         elif k == "shl32":
             _, d, a, n = ins
             env[d] = (val(a) << n) & M32
@@ -319,8 +335,10 @@ def _check_cover(chains_e, chains_o, square):
     assert seen == want, (sorted(want - seen), sorted(seen - want))
 
 
-def emit_products(g, chains_e, chains_o, xa, xb, tops):
-    """Emit the product chains.  Returns the set of registers that hold a value afterwards."""
+def emit_products(g, chains_e, chains_o, xa, xb, tops, fresh_hook=None):
+    """Emit the product chains.  Returns the set of registers that hold a value afterwards.
+    fresh_hook(list of (i, j, hi register)) is called after every chain whose products all landed
+    on untouched pairs: there the registers hold the exact products a_i*b_j."""
     touched = set()       # registers holding a value
     deposit_only = set()  # ... that so far hold nothing but a deposited carry (0/1)
 
@@ -358,7 +376,12 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops):
                 touched.add(lo); touched.add(hi)
                 deposit_only.discard(lo)
             g.end()
+            if allfresh and fresh_hook is not None:
+                fresh_hook([(i, j, R(acc, w + 1)) for (w, i, j) in ch])
     return touched
+
+
+PIN_M0 = True
 
 
 def emit_reduction(g, T):
@@ -367,6 +390,11 @@ def emit_reduction(g, T):
         m = low256(T + (m<<96) + (m<<192) - (m<<224))
     and the quotient is t = (T + (m<<96) + (m<<192) - (m<<224) + (m<<256)) >> 256, nine words
     h0..h8 (h8 is 0 or 1); the conditional subtraction of p is left to the caller."""
+    if PIN_M0:
+        # ptxas otherwise re-computes the low word of a0*b0 with an extra IMAD at each of its four uses
+        # (it is cheaper than a register in its cost model); adding a zero it cannot see through pins it.
+        g.raw("m0 = %s + ecb200_opaque_zero();" % T[0], ("copy", "m0", T[0]), regs=["m0"])
+        T = ["m0"] + list(T[1:])
     m = ["%s" % T[0], "%s" % T[1], "%s" % T[2], "m3", "m4", "m5", "m6", "m7"]
     # low words of +(m<<192) and -(m<<224): they need only m0, m1
     g.begin()
@@ -448,7 +476,23 @@ def gen_mul512():
 def gen_sqr():
     _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
     g = Emit()
-    touched = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None})
+    g.exact_pairs = []   # cross products whose high word is observed exactly (see fp_sqr_quirk_filter)
+    state = {"have": False}
+
+    def hook(items):
+        # qx = signed max of the exact high words hi32(a_i*a_j): INT_MAX <=> that pair is in the
+        # reference's lost-carry set (fp256.cuh); three values per VIMNMX3
+        regs = [r for (_, _, r) in items]
+        g.exact_pairs.extend((i, j) for (i, j, _) in items)
+        while regs:
+            take = regs[:2] if state["have"] else regs[:3]
+            regs = regs[len(take):]
+            args = (["qx"] if state["have"] else []) + take
+            while len(args) < 3:
+                args.append(args[-1])
+            g.raw("qx = (uint32_t)__vimax3_s32((int)%s, (int)%s, (int)%s);" % tuple(args), ("max3s", "qx") + tuple(args), regs=["qx"])
+            state["have"] = True
+    touched = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None}, fresh_hook=hook)
     # cross sum S = E + O: words 1..14, carry into word 15
     g.begin()
     for w in range(1, 15):
@@ -506,6 +550,11 @@ def check(g, unary=False, ntests=3000, seed=1):
             env["b%d" % k] = (y >> (32 * k)) & M32
         simulate(g.ir, env)
         got = sum(env["h%d" % k] << (32 * k) for k in range(9))
+        if unary and getattr(g, "exact_pairs", None):
+            def sgn(v):
+                return v - 2**32 if v >= 2**31 else v
+            want_qx = max(sgn((env["a%d" % i] * env["a%d" % j]) >> 32) for (i, j) in g.exact_pairs) & M32
+            assert env["qx"] == want_qx, "qx mismatch"
         T = x * y
         m = (-T * pinv) % 2**256
         want = (T + m * P) >> 256
@@ -535,6 +584,11 @@ HEADER = """// GENERATED by gen_fp256.py -- do not edit by hand; edit the genera
 #include <cstdint>
 
 namespace ecb200 {
+
+// A zero the compiler cannot see through (a __constant__ word nobody writes): used to pin values
+// that ptxas would otherwise rematerialise with extra multiplies.
+__constant__ uint32_t g_ecb200_opaque_zero;
+__device__ __forceinline__ uint32_t ecb200_opaque_zero() { return g_ecb200_opaque_zero; }
 
 """
 
@@ -570,7 +624,9 @@ def emit_header(path):
             env["b%d" % k] = (y >> (32 * k)) & M32
         simulate(g5.ir, env)
         assert sum(env["t%d" % k] << (32 * k) for k in range(16)) == x * y
-    txt = (HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1) +
+    txt = (HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1, outs=["h%d" % k for k in range(9)] + ["qx"]) +
+           "// cross products (i, j) whose exact high word enters qx above\n" +
+           "#define ECB200_SQR_EXACT_PAIRS {%s}\n\n" % ", ".join("{%d, %d}" % ij for ij in gs.exact_pairs) +
            "// T = a*b, the exact 512-bit product (mul.h:150-158), 16 words\n" +
            _emit_fn("fp_mul512_words", g5, 2, outs=["t%d" % k for k in range(16)]) + "}  // namespace ecb200\n")
     with open(path, "w") as f:

@@ -64,6 +64,9 @@ __device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O, MD& md) {
 
 // ZDAU core on bare coordinates: (X1,Y1) <- 2*(X1,Y1) + (X2,Y2); (X2,Y2) <- the same
 // point (X2,Y2) re-scaled to the new common Z; Z <- new Z.
+#ifndef ECB200_ZDAU_GROUPS
+#define ECB200_ZDAU_GROUPS 0
+#endif
 #ifndef ECB200_ZDAU_ORDER
 #define ECB200_ZDAU_ORDER 1
 #endif
@@ -101,21 +104,28 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe X2n = fp_sub(Dc, W12);
   const fe Y2n = fp_sub(fp_mul(yp, fp_sub(W1, X2n), md), A1);
 #else
-  // Same values, statement order chosen so that consecutive multiplications are independent:
-  // ptxas then overlaps the IMAD.WIDE products of one with the carry-chain reduction of the
-  // previous one (tools/sass_sim.py; the two pipes otherwise take turns).
+  // Same values, statement order chosen so that consecutive multiplications are independent
+  // (ptxas then overlaps their carry chains), and the squarings grouped so that one branch
+  // resolves the squaring-defect filter of a whole group (fp_sqr_acc / fp_quirk_check).
   const fe dx = fp_sub(X1, X2);
   const fe dy = fp_sub(Y1, Y2);
-  const fe Cp = fp_sqr<QUIRK>(dx, md);
-  const fe Dp = fp_sqr<QUIRK>(dy, md);
+  uint32_t f1 = 0xffffffffu;
+  const fe Cp = fp_sqr_acc<QUIRK>(dx, md, f1);
+  const fe Dp = fp_sqr_acc<QUIRK>(dy, md, f1);
+  fp_quirk_check<QUIRK>(md, f1, dx, dy);
   const fe W1p = fp_mul(X1, Cp, md);
   const fe W2p = fp_mul(X2, Cp, md);
   const fe A1p = fp_mul(Y1, fp_sub(W1p, W2p), md);
   const fe X3pc = fp_sub(fp_sub(Dp, W1p), W2p);
   const fe e3 = fp_sub(X3pc, W1p);
-  const fe C = fp_sqr<QUIRK>(e3, md);
-  const fe s4 = fp_sqr<QUIRK>(fp_sub(dy, e3), md);         // ((Y1-Y2) + (W1p-X3pc))^2, (W1p - X3pc) = -e3
-  const fe s6 = fp_sqr<QUIRK>(fp_add(dx, e3, md), md);     // (X1 - X2 + X3pc - W1p)^2
+  const fe de = fp_sub(dy, e3);                            // (Y1-Y2) + (W1p-X3pc), (W1p - X3pc) = -e3
+  const fe xe = fp_add(dx, e3, md);                        // X1 - X2 + X3pc - W1p
+#if ECB200_ZDAU_GROUPS == 0
+  uint32_t f2 = 0xffffffffu;
+  const fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
+  const fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
+  const fe s6 = fp_sqr_acc<QUIRK>(xe, md, f2);
+  fp_quirk_check<QUIRK>(md, f2, e3, de, xe);
   const fe C4 = fp_shl<2>(C, md);                          // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once
   const fe W1 = fp_mul(X3pc, C4, md);
   const fe W2 = fp_mul(W1p, C4, md);
@@ -125,8 +135,30 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe Y3p = fp_sub(fp_sub(fp_sub(s4, Dp), C), A2);
   const fe ym = fp_sub(Y3p, A2);
   const fe yp = fp_add(Y3p, A2, md);
-  const fe D = fp_sqr<QUIRK>(ym, md);
-  const fe Dc = fp_sqr<QUIRK>(yp, md);
+  uint32_t f3 = 0xffffffffu;
+  const fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
+  const fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
+  fp_quirk_check<QUIRK>(md, f3, ym, yp);
+#else
+  uint32_t f2 = 0xffffffffu;
+  const fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
+  const fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
+  fp_quirk_check<QUIRK>(md, f2, e3, de);
+  const fe C4 = fp_shl<2>(C, md);                          // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once
+  const fe W1 = fp_mul(X3pc, C4, md);
+  const fe W2 = fp_mul(W1p, C4, md);
+  if (MIDSYNC) { if (grp == 1) asm volatile("bar.sync 0;" ::: "memory"); }
+  const fe A2 = fp_shl1(A1p, md);
+  const fe Y3p = fp_sub(fp_sub(fp_sub(s4, Dp), C), A2);
+  const fe ym = fp_sub(Y3p, A2);
+  const fe yp = fp_add(Y3p, A2, md);
+  uint32_t f3 = 0xffffffffu;
+  const fe s6 = fp_sqr_acc<QUIRK>(xe, md, f3);
+  const fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
+  const fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
+  fp_quirk_check<QUIRK>(md, f3, xe, ym, yp);
+  const fe Z3 = fp_mul(Z, fp_sub(fp_sub(s6, Cp), C), md);
+#endif
   const fe A1 = fp_mul(Y3p, fp_sub(W1, W2), md);
   const fe W12 = fp_add(W1, W2, md);
   const fe X3 = fp_sub(D, W12);
