@@ -7,6 +7,7 @@
 // (211 540 MAC32 per lane against 224 bytes of traffic), so the conversion passes are
 // noise there.
 #include <cstdlib>
+#include <mutex>
 
 #include "host_common.cuh"
 #include "layout.cuh"
@@ -71,33 +72,75 @@ __global__ void __launch_bounds__(128) k_point(void* out1, void* out2, const voi
   else point_store<OP>(out1, out2, n, i, r, w);
 }
 
-// The ladder kernel.  mode 0: per-lane point P[i]; mode 1: P = G for every lane; the scalar is per
-// lane unless k_bcast (scalar_mult_1s: one scalar for all lanes).  One block of 512 threads per SM
-// (16 warps, 128 registers each), all warps kept in step by a barrier per ladder iteration: the
-// ~52 KB loop body is then fetched once per SM instead of once per warp.
+// The ladder kernel.  mode 0: per-lane point P[i]; mode 1: P = G for every lane (with TABW > 0 the
+// ladder starts from the table of states after TABW bits); the scalar is per lane unless k_bcast
+// (scalar_mult_1s: one scalar for all lanes).  One block of 512 threads per SM (16 warps, 128
+// registers each), all warps kept in step by a barrier per ladder iteration: the ~50 KB loop body
+// is then fetched once per SM instead of once per warp.
 // L: layout of k, P and out -- the ladder reads 128 and writes 96 bytes per lane, so it takes the
 // caller's layout directly (no conversion pass, no extra kernels competing for the SMs).
-template <bool QUIRK, int MODE, int THREADS, int L>
+// Scalar words and P are re-read from memory where they are needed (SrcGlobal) rather than held
+// in registers through the loop.
+template <int MODE, int L>
+struct SrcGlobal {
+  const void* k;
+  const void* P;
+  const uint4* tab;
+  size_t n, i;
+  int k_bcast;
+  __device__ __forceinline__ uint32_t kword(int w) const {
+    return k_bcast ? Layout<L_LANE>::load_word(k, 1, 0, 1, 0, w) : Layout<L>::load_word(k, n, i, 1, 0, w);
+  }
+  __device__ __forceinline__ void point(fe& x, fe& y) const {
+    if (MODE == 0) {
+      const void* p = P;
+      asm volatile("" : "+l"(p));  // a fresh load each time: the value is not kept live through the loop
+      x = Layout<L>::load(p, n, i, 3, 0);
+      y = Layout<L>::load(p, n, i, 3, 1);
+    } else {
+      const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
+      x = fe_const(gx);
+      y = fe_const(gy);
+    }
+  }
+  __device__ __forceinline__ void table(uint32_t idx, fe (&st)[5]) const {
+    const uint4* e = tab + (size_t)idx * 10;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      const uint4 lo = __ldg(e + 2 * c), hi = __ldg(e + 2 * c + 1);
+      st[c].v[0] = lo.x; st[c].v[1] = lo.y; st[c].v[2] = lo.z; st[c].v[3] = lo.w;
+      st[c].v[4] = hi.x; st[c].v[5] = hi.y; st[c].v[6] = hi.z; st[c].v[7] = hi.w;
+    }
+  }
+};
+
+template <bool QUIRK, int MODE, int THREADS, int L, int TABW>
 __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restrict__ out, const void* __restrict__ k,
-                                                                 const void* __restrict__ P, size_t n, int k_bcast) {
+                                                                 const void* __restrict__ P, size_t n, int k_bcast,
+                                                                 const uint4* __restrict__ tab) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = i0 < n ? i0 : n - 1;  // surplus threads recompute the last lane (they must reach the barriers)
-  const fe kk = k_bcast ? Layout<L_LANE>::load(k, 1, 0, 1, 0) : Layout<L>::load(k, n, i, 1, 0);
-  fe px, py;
-  if (MODE == 0) {
-    px = Layout<L>::load(P, n, i, 3, 0);
-    py = Layout<L>::load(P, n, i, 3, 1);
-  } else {
-    const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
-    px = fe_const(gx);
-    py = fe_const(gy);
-  }
-  const jac r = pt_scalar_mult<QUIRK, true>(kk.v, px, py);
+  const SrcGlobal<MODE, L> src{k, P, tab, n, i, k_bcast};
+  const jac r = pt_scalar_mult<QUIRK, true, TABW>(src);
   if (i0 < n) {
     Layout<L>::store(out, n, i, 3, 0, r.x);
     Layout<L>::store(out, n, i, 3, 1, r.y);
     Layout<L>::store(out, n, i, 3, 2, r.z);
   }
+}
+
+// Fixed-base table: entry idx (TABW bits) = ladder state of G after the steps for scalar bits
+// 1..TABW = idx, five field elements (base.x, base.y, P.x, P.y, Z) of 32 bytes each.
+template <bool QUIRK>
+__global__ void __launch_bounds__(128) k_build_base_table(uint4* __restrict__ tab, int tabw) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (1u << tabw)) return;
+  const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
+  uint32_t xy[16], st[40];
+  for (int j = 0; j < 8; j++) { xy[j] = gx[j]; xy[8 + j] = gy[j]; }
+  pt_ladder_prefix_exact<QUIRK>(st, idx, tabw, xy);
+  uint4* e = tab + (size_t)idx * 10;
+  for (int c = 0; c < 10; c++) e[c] = make_uint4(st[4 * c], st[4 * c + 1], st[4 * c + 2], st[4 * c + 3]);
 }
 
 template <bool QUIRK>
@@ -245,18 +288,58 @@ constexpr int kLadderThreads = 512;
 // Layouts with a native ladder instance (bit-exact mode only: the NO_QUIRK variants exist for SOA).
 static bool ladder_has_layout(int L, bool q) { return L == L_SOA || q; }
 
+// Fixed-base table (BASELINE config 4): 2^kBaseTabW ladder states of G, 160 bytes each (10 MiB:
+// resident in the 126 MB L2 while a batch runs), built on first use per device and quirk mode.
+// ECB200_BASE_TABLE=0 in the environment selects the plain ladder with P = G.
+constexpr int kBaseTabW = 16;
+struct BaseTable {
+  uint4* tab[2] = {nullptr, nullptr};  // [quirk]
+  int device = -1;
+};
+static int base_table(bool q, cudaStream_t s, const uint4** out) {
+  static std::mutex mu;
+  static BaseTable bt[16];
+  static const bool enabled = [] { const char* e = getenv("ECB200_BASE_TABLE"); return !(e && e[0] == '0'); }();
+  *out = nullptr;
+  if (!enabled) return ECB200_OK;
+  int dev = 0;
+  ECB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return ECB200_OK;
+  std::lock_guard<std::mutex> lock(mu);
+  BaseTable& b = bt[dev];
+  if (!b.tab[q]) {
+    uint4* t = nullptr;
+    ECB_CUDA(cudaMalloc(&t, ((size_t)1 << kBaseTabW) * 160));
+    const unsigned blocks = (1u << kBaseTabW) / 128;
+    if (q) k_build_base_table<true><<<blocks, 128, 0, s>>>(t, kBaseTabW);
+    else k_build_base_table<false><<<blocks, 128, 0, s>>>(t, kBaseTabW);
+    ECB_LAUNCH_CHECK();
+    ECB_CUDA(cudaStreamSynchronize(s));  // other streams may use the table from now on
+    b.tab[q] = t;
+  }
+  *out = b.tab[q];
+  return ECB200_OK;
+}
+
 template <bool Q, int L>
-static int launch_ladder_ql(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, cudaStream_t s) {
+static int launch_ladder_ql(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, cudaStream_t s, bool use_table) {
   const unsigned blocks = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
-  if (mode == 0) k_scalar_mult_sync<Q, 0, kLadderThreads, L><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
-  else k_scalar_mult_sync<Q, 1, kLadderThreads, L><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast);
+  if (mode == 0) {
+    k_scalar_mult_sync<Q, 0, kLadderThreads, L, 0><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, nullptr);
+  } else {
+    const uint4* tab = nullptr;
+    int rc = use_table ? base_table(Q, s, &tab) : ECB200_OK;
+    if (rc) return rc;
+    if (tab) k_scalar_mult_sync<Q, 1, kLadderThreads, L, kBaseTabW><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, tab);
+    else k_scalar_mult_sync<Q, 1, kLadderThreads, L, 0><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, nullptr);
+  }
   ECB_LAUNCH_CHECK();
   return ECB200_OK;
 }
-static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s) {
-  if (L == L_SOA) return q ? launch_ladder_ql<true, L_SOA>(dout, dk, dP, mode, k_bcast, n, s) : launch_ladder_ql<false, L_SOA>(dout, dk, dP, mode, k_bcast, n, s);
-  if (L == L_LANE && q) return launch_ladder_ql<true, L_LANE>(dout, dk, dP, mode, k_bcast, n, s);
-  if (L == L_PACK4 && q) return launch_ladder_ql<true, L_PACK4>(dout, dk, dP, mode, k_bcast, n, s);
+static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s, bool use_table = true) {
+  if (L == L_SOA) return q ? launch_ladder_ql<true, L_SOA>(dout, dk, dP, mode, k_bcast, n, s, use_table) : launch_ladder_ql<false, L_SOA>(dout, dk, dP, mode, k_bcast, n, s, use_table);
+  if (L == L_LANE && q) return launch_ladder_ql<true, L_LANE>(dout, dk, dP, mode, k_bcast, n, s, use_table);
+  if (L == L_PACK4 && q) return launch_ladder_ql<true, L_PACK4>(dout, dk, dP, mode, k_bcast, n, s, use_table);
   set_error("internal: no ladder instance for layout %d", L);
   return ECB200_ERR_ARG;
 }
@@ -285,6 +368,7 @@ static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, i
   const int L = layout_of(flags);
   const bool q = quirk_on(flags);
   const bool native = ladder_has_layout(L, q);
+  const bool use_table = (flags & ECB200_NO_BASE_TABLE) == 0;
   cudaStream_t* ss = nullptr;
   int rc = pipe_streams(&ss);
   if (rc) return rc;
@@ -303,7 +387,7 @@ static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, i
       ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
     }
     if (native) {
-      if ((rc = launch_ladder(L, ro, rk, rP, mode, 0, m, q, s))) return rc;
+      if ((rc = launch_ladder(L, ro, rk, rP, mode, 0, m, q, s, use_table))) return rc;
     } else {
       void *sk, *sP = nullptr, *so;
       if ((rc = sc.alloc(&sk, operand_bytes(m, 1))) || (rc = sc.alloc(&so, operand_bytes(m, 3)))) return rc;
@@ -312,7 +396,7 @@ static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, i
         if ((rc = sc.alloc(&sP, operand_bytes(m, 3)))) return rc;
         if ((rc = convert_to_soa(L, sP, rP, m, 3, s))) return rc;
       }
-      if ((rc = launch_ladder(L_SOA, so, sk, sP, mode, 0, m, q, s))) return rc;
+      if ((rc = launch_ladder(L_SOA, so, sk, sP, mode, 0, m, q, s, use_table))) return rc;
       if ((rc = convert_from_soa(L, ro, so, m, 3, s))) return rc;
     }
     ECB_CUDA(cudaMemcpyAsync((char*)out + lo * 96, ro, operand_bytes(m, 3), cudaMemcpyDeviceToHost, s));
@@ -346,7 +430,7 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
   } else if ((rc = st.in(k, 1, &dk))) return rc;
   if (mode == 0 && (rc = st.in(P, 3, &dP))) return rc;
   if ((rc = st.out(out, 3, &dout))) return rc;
-  if ((rc = launch_ladder(native ? L : L_SOA, dout, dk, dP, mode, k_bcast, n, q, st.s))) return rc;
+  if ((rc = launch_ladder(native ? L : L_SOA, dout, dk, dP, mode, k_bcast, n, q, st.s, (flags & ECB200_NO_BASE_TABLE) == 0))) return rc;
   return st.finish();
 }
 

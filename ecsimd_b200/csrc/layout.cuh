@@ -30,6 +30,10 @@ struct Layout<L_LANE> {
     p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
     p[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
   }
+  // 32-bit word w (0..7) of value i
+  static __device__ __forceinline__ uint32_t load_word(const void* base, size_t n, size_t i, int nc, int c, int w) {
+    return __ldg(reinterpret_cast<const uint32_t*>(base) + (i * nc + c) * 8 + w);
+  }
 };
 
 // the reference's wide<bignum_256> pack: u64 word index inside a pack = limb*4 + lane
@@ -52,6 +56,10 @@ struct Layout<L_PACK4> {
 #pragma unroll
     for (int l = 0; l < 4; l++) p[4 * l] = make_uint2(a.v[2 * l], a.v[2 * l + 1]);
   }
+  static __device__ __forceinline__ uint32_t load_word(const void* base, size_t n, size_t i, int nc, int c, int w) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(base) + ((i >> 2) * nc + c) * 16 + (i & 3) + 4 * (w >> 1));
+    return __ldg(p + (w & 1));
+  }
 };
 
 // planar: plane (2c) holds words 0..3 of coordinate c for all lanes, plane (2c+1) words 4..7
@@ -69,6 +77,10 @@ struct Layout<L_SOA> {
     uint4* p = reinterpret_cast<uint4*>(base) + (size_t)(2 * c) * n + i;
     p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
     p[n] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  }
+  static __device__ __forceinline__ uint32_t load_word(const void* base, size_t n, size_t i, int nc, int c, int w) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint4*>(base) + (size_t)(2 * c + (w >> 2)) * n + i);
+    return __ldg(p + (w & 3));
   }
 };
 

@@ -212,33 +212,71 @@ __device__ __forceinline__ jac pt_trplu(jac& P, MD& md) {
 // opening swap of step b+1 are merged into one swap on (bit_b xor bit_{b+1}).
 // SYNC: all warps of the block meet at a barrier once per ladder step, so that they walk
 // the (large, fully unrolled) loop body together and share instruction-cache lines.
-template <bool QUIRK, bool SYNC, class MD>
-__device__ __forceinline__ jac pt_scalar_mult_mode(const uint32_t (&k)[8], const fe& Px, const fe& Py, MD& md) {
-  jac P;
-  P.x = Px; P.y = Py; P.z = fe_R();
-  const fe oppY = fp_neg(Py);
-  jac base = pt_trplu<QUIRK>(P, md);
-  fe Z = base.z;
-  // state: (base.x, base.y) and (P.x, P.y) share Z.
-  uint32_t prev = (k[0] >> 1) & 1u;  // pending swap
-  uint32_t w = k[0] >> 2;
+//
+// Inputs come through a source object instead of registers: the loop needs one scalar word every
+// 32 steps and P only before and after it, so holding them (24 registers) through 254 steps only
+// costs spills.  Src provides
+//     uint32_t kword(int w) const;                 word w of the scalar
+//     void point(fe& x, fe& y) const;              P (affine Montgomery coordinates, Z = R)
+//     void table(uint32_t idx, fe (&st)[5]) const; ladder state after bits 1..TABW (TABW > 0 only)
+// TABW > 0 (fixed base point): the state (base.x, base.y, P.x, P.y, Z) after the steps for bits
+// 1..TABW depends only on those bits, so it is looked up and the ladder resumes at bit TABW+1:
+// same values as the full ladder, because the ladder is right-to-left.
+struct SrcRegs {
+  const uint32_t* k;
+  const uint32_t* xy;  // x words 0..7, y words 8..15
+  __device__ __forceinline__ uint32_t kword(int w) const { return k[w]; }
+  __device__ __forceinline__ void point(fe& x, fe& y) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x.v[i] = xy[i]; y.v[i] = xy[8 + i]; }
+  }
+  __device__ __forceinline__ void table(uint32_t, fe (&)[5]) const {}
+};
+
+template <bool QUIRK, bool SYNC, int TABW, class MD, class Src>
+__device__ __forceinline__ jac pt_scalar_mult_mode(const Src& src, MD& md) {
+  static_assert(TABW >= 0 && TABW <= 30, "table index comes from the low scalar word");
+  fe bx, by, qx, qy, Z;  // (bx, by) = base, (qx, qy) = P of the reference's loop; they share Z
+  const uint32_t k0 = src.kword(0);
+  uint32_t prev, w;
+  int b0;
+  if (TABW == 0) {
+    jac P;
+    src.point(P.x, P.y);
+    P.z = fe_R();
+    const jac base = pt_trplu<QUIRK>(P, md);
+    bx = base.x; by = base.y; qx = P.x; qy = P.y; Z = base.z;
+    prev = (k0 >> 1) & 1u;  // pending swap
+    w = k0 >> 2;
+    b0 = 2;
+  } else {
+    fe st[5];
+    src.table((k0 >> 1) & ((1u << TABW) - 1u), st);
+    bx = st[0]; by = st[1]; qx = st[2]; qy = st[3]; Z = st[4];
+    prev = (k0 >> TABW) & 1u;
+    b0 = TABW + 1;
+    w = src.kword(b0 >> 5) >> (b0 & 31);
+  }
 #pragma unroll 1
-  for (int b = 2; b < 256; b++) {
-    if ((b & 31) == 0) w = k[b >> 5];
+  for (int b = b0; b < 256; b++) {
+    if ((b & 31) == 0) w = src.kword(b >> 5);
     const uint32_t bit = w & 1u;
     w >>= 1;
     const uint32_t sw = prev ^ bit;
-    fe_cswap(sw, P.x, base.x);
-    fe_cswap(sw, P.y, base.y);
-    pt_zdau_xy<QUIRK>(base.x, base.y, P.x, P.y, Z, md);
+    fe_cswap(sw, qx, bx);
+    fe_cswap(sw, qy, by);
+    pt_zdau_xy<QUIRK>(bx, by, qx, qy, Z, md);
     prev = bit;
     if (SYNC) __syncthreads();
   }
-  fe_cswap(prev, P.x, base.x);
-  fe_cswap(prev, P.y, base.y);
-  P.z = Z;
-  const jac Psub = pt_add_z2_1<QUIRK>(P, Px, oppY, md);
-  const bool odd = (k[0] & 1u) != 0u;
+  fe_cswap(prev, qx, bx);
+  fe_cswap(prev, qy, by);
+  jac P;
+  P.x = qx; P.y = qy; P.z = Z;
+  fe Px, Py;
+  src.point(Px, Py);
+  const jac Psub = pt_add_z2_1<QUIRK>(P, Px, fp_neg(Py), md);
+  const bool odd = (src.kword(0) & 1u) != 0u;
   jac out;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -253,21 +291,49 @@ __device__ __forceinline__ jac pt_scalar_mult_mode(const uint32_t (&k)[8], const
 // rare case resolved in place.  Kept out of line so that it costs the hot path nothing.
 template <bool QUIRK>
 __device__ __noinline__ void pt_scalar_mult_exact(uint32_t* out24, const uint32_t* k8, const uint32_t* xy16) {
-  uint32_t k[8];
-  fe px, py;
-  for (int i = 0; i < 8; i++) { k[i] = k8[i]; px.v[i] = xy16[i]; py.v[i] = xy16[8 + i]; }
   Exact md;
-  const jac r = pt_scalar_mult_mode<QUIRK, false>(k, px, py, md);
+  const SrcRegs src{k8, xy16};
+  const jac r = pt_scalar_mult_mode<QUIRK, false, 0>(src, md);
   for (int i = 0; i < 8; i++) { out24[i] = r.x.v[i]; out24[8 + i] = r.y.v[i]; out24[16 + i] = r.z.v[i]; }
 }
 
-template <bool QUIRK, bool SYNC = false>
-__device__ __forceinline__ jac pt_scalar_mult(const uint32_t (&k)[8], const fe& Px, const fe& Py) {
+// Ladder state after the steps for bits 1..tabw of the scalar `bits << 1` on point (px, py), every
+// rare case resolved in place: one entry of the fixed-base table.
+template <bool QUIRK>
+__device__ __noinline__ void pt_ladder_prefix_exact(uint32_t* st40, uint32_t bits, int tabw, const uint32_t* xy16) {
+  Exact md;
+  jac P;
+  for (int i = 0; i < 8; i++) { P.x.v[i] = xy16[i]; P.y.v[i] = xy16[8 + i]; }
+  P.z = fe_R();
+  const jac base = pt_trplu<QUIRK>(P, md);
+  fe bx = base.x, by = base.y, qx = P.x, qy = P.y, Z = base.z;
+  uint32_t prev = bits & 1u;  // bit 1 of the scalar
+  uint32_t w = bits >> 1;
+#pragma unroll 1
+  for (int b = 2; b <= tabw; b++) {
+    const uint32_t bit = w & 1u;
+    w >>= 1;
+    const uint32_t sw = prev ^ bit;
+    fe_cswap(sw, qx, bx);
+    fe_cswap(sw, qy, by);
+    pt_zdau_xy<QUIRK>(bx, by, qx, qy, Z, md);
+    prev = bit;
+  }
+  for (int i = 0; i < 8; i++) {
+    st40[i] = bx.v[i]; st40[8 + i] = by.v[i]; st40[16 + i] = qx.v[i]; st40[24 + i] = qy.v[i]; st40[32 + i] = Z.v[i];
+  }
+}
+
+// Fast ladder (Lazy mode) with the exact re-run of flagged lanes.
+template <bool QUIRK, bool SYNC, int TABW, class Src>
+__device__ __forceinline__ jac pt_scalar_mult(const Src& src) {
   Lazy md;
-  jac r = pt_scalar_mult_mode<QUIRK, SYNC>(k, Px, Py, md);
+  jac r = pt_scalar_mult_mode<QUIRK, SYNC, TABW>(src, md);
   if (__builtin_expect(md.flagged(), 0)) {
     uint32_t kk[8], xy[16], o[24];
-    for (int i = 0; i < 8; i++) { kk[i] = k[i]; xy[i] = Px.v[i]; xy[8 + i] = Py.v[i]; }
+    fe px, py;
+    src.point(px, py);
+    for (int i = 0; i < 8; i++) { kk[i] = src.kword(i); xy[i] = px.v[i]; xy[8 + i] = py.v[i]; }
     pt_scalar_mult_exact<QUIRK>(o, kk, xy);
     for (int i = 0; i < 8; i++) { r.x.v[i] = o[i]; r.y.v[i] = o[8 + i]; r.z.v[i] = o[16 + i]; }
   }

@@ -59,8 +59,8 @@ def scalar_mult(out, k, P, n, layout="soa", quirk=True):
     return out
 
 
-def scalar_mult_base(out, k, n, layout="soa", quirk=True):
-    capi.call("ecb200_scalar_mult_p256_base", out.data_ptr(), k.data_ptr(), n, _flags(layout, quirk), _stream())
+def scalar_mult_base(out, k, n, layout="soa", quirk=True, table=True):
+    capi.call("ecb200_scalar_mult_p256_base", out.data_ptr(), k.data_ptr(), n, _flags(layout, quirk) | (0 if table else 0x200), _stream())
     return out
 
 

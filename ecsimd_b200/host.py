@@ -108,12 +108,13 @@ def scalar_mult(k, P, layout="lane", quirk=True):
 scalar_mult_p256 = scalar_mult  # lib/scalar_mult_p256.cpp:12-14
 
 
-def scalar_mult_base(k, layout="lane", quirk=True):
-    """scalar_mult(x, WJG()): the generator for every lane (curve_group.h:39-41)"""
+def scalar_mult_base(k, layout="lane", quirk=True, table=True):
+    """scalar_mult(x, WJG()): the generator for every lane (curve_group.h:39-41).
+    table=False runs the plain ladder instead of starting from the fixed-base table (same results)."""
     k = _in(k)
     n = lanes_of(k, layout, 1)
     out = np.zeros(_shape(layout, n, 3), np.uint32)
-    capi.call("ecb200_scalar_mult_p256_base", capi._p(out), capi._p(k), n, _flags(layout, quirk), None)
+    capi.call("ecb200_scalar_mult_p256_base", capi._p(out), capi._p(k), n, _flags(layout, quirk) | (0 if table else 0x200), None)
     return out
 
 

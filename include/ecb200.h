@@ -74,6 +74,9 @@ extern "C" {
 #define ECB200_MEM_DEVICE 0x10u
 #define ECB200_MEM_MASK 0x10u
 #define ECB200_NO_QUIRK 0x100u
+/* ecb200_scalar_mult_p256_base only: run the plain ladder on G instead of starting from the
+ * fixed-base table of ladder states (same results; for A/B measurements and tests). */
+#define ECB200_NO_BASE_TABLE 0x200u
 
 /* ---- library ------------------------------------------------------------- */
 int ecb200_abi_version(void);

@@ -65,3 +65,6 @@ def test_generator_2p24(eng, orc):
     out2 = dev.scalar_mult_base(dev.empty(n, 3), k, n)
     assert np.array_equal(dev.checksum(out2), c1)
     assert torch.equal(out, out2)
+    # the fixed-base table (all 2^16 indices occur among 2^24 random scalars) against the plain ladder
+    out3 = dev.scalar_mult_base(dev.empty(n, 3), k, n, table=False)
+    assert torch.equal(out, out3)

@@ -99,6 +99,27 @@ def test_scalar_mult_base_and_1s(eng, orc):
     assert np.array_equal(eng.scalar_mult_1s(k1, P), orc.scalar_mult(np.repeat(k1[None], n, axis=0), P))
 
 
+def test_scalar_mult_base_table(eng, orc):
+    """Fixed-base table of ladder states (BASELINE config 4): starting the right-to-left
+    ladder from the looked-up state after 16 bits gives the reference's Jacobian (X, Y, Z) bit for bit."""
+    rnd = np.random.RandomState(5)
+    ks = [_libs.to_ints(raw256(123, 1))[0]]
+    # edge scalars, small scalars (every low-bit pattern matters for the table index), top bits set
+    ks += _libs.EDGE_SCALARS + list(range(0, 40)) + [(1 << 17) - 1, 1 << 16, 1 << 17, (1 << 17) + 1, (1 << 256) - (1 << 17)]
+    ks += [int(x) << 1 | int(b) for x in rnd.randint(0, 1 << 16, size=64) for b in (0, 1)]          # table index = bits 1..16
+    ks += [(_libs.to_ints(raw256(9, 1, start=i))[0] & ~0x1FFFF) | int(rnd.randint(0, 1 << 17)) for i in range(64)]
+    k = to_words(ks)
+    k = np.concatenate([k, raw256(321, (-len(k)) % 4 + 128)])
+    n = len(k)
+    G = np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)
+    want = orc.scalar_mult(k, orc.from_affine(np.repeat(G, n, axis=0)))
+    assert np.array_equal(eng.scalar_mult_base(k), want)
+    assert np.array_equal(eng.scalar_mult_base(k, table=False), want)
+    for layout, conv in (("pack4", (eng.lane_to_pack4, eng.pack4_to_lane)), ("soa", (eng.lane_to_soa, eng.soa_to_lane))):
+        assert np.array_equal(conv[1](eng.scalar_mult_base(conv[0](k, 1), layout=layout), 3), want)
+    assert np.array_equal(eng.scalar_mult_base(k, quirk=False), eng.scalar_mult_base(k, quirk=False, table=False))
+
+
 @pytest.mark.parametrize("layout", ["pack4", "soa"])
 def test_scalar_mult_layouts(eng, orc, pts, layout):
     n = 64
