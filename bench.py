@@ -251,7 +251,7 @@ def main():
     ms = shard.max_over_ranks(ms_local, cuda if world > 1 else None)
     lanes_total = shard.sum_over_ranks(n, cuda if world > 1 else None)
     value = lanes_total * args.steps / (ms * 1e-3)
-    kernel_ms = ms_local / args.steps                      # one kernel launch per step on this path
+    kernel_ms = ms_local / args.steps                      # one ladder kernel launch per step on this path
     achieved = n * MAC32_PER_SCALAR_MULT / (kernel_ms * 1e-3)
 
     # ---- parity spot check against the CPU oracle (checker only; not timed) -------------------------
@@ -350,17 +350,33 @@ def main():
         dev.trplu(Q2, R2, P2, n2); torch.cuda.synchronize()
         t_trplu = timed(lambda: dev.trplu(Q2, R2, P2, n2), 3)
         t_zdau = timed(lambda: dev.zdau(O2, J2, R2, Q2, n2), 3)
+        t_dblu = timed(lambda: dev.dblu(O2, J2, P2, n2), 3)        # (P', 2P) with a common Z
+        t_zaddu = timed(lambda: dev.zaddu(Q2, R2, O2, J2, n2), 3)  # ZADDU on that co-Z pair
+        t_addz = timed(lambda: dev.add_z2_1(O2, R2, P2, n2), 3)    # mixed add with a Z = R point
+
+        def _po(t, mac, nbytes):
+            return {"ms": t, "points_per_s": n2 / t * 1e3, "GBps": n2 * nbytes / t * 1e3 / 1e9, "TMAC32_per_s": n2 * mac / t * 1e3 / 1e12,
+                    "frac_of_hbm_peak": n2 * nbytes / t * 1e3 / 1e9 / hbm_peak, "frac_of_imad_peak": n2 * mac / t * 1e3 / peak_wide}
         aux["point_ops_2^22"] = {
-            "trplu": {"ms": t_trplu, "points_per_s": n2 / t_trplu * 1e3, "GBps": n2 * 288 / t_trplu * 1e3 / 1e9, "TMAC32_per_s": n2 * 636 / t_trplu * 1e3 / 1e12},
-            "zdau": {"ms": t_zdau, "points_per_s": n2 / t_zdau * 1e3, "GBps": n2 * 384 / t_zdau * 1e3 / 1e9, "TMAC32_per_s": n2 * 828 / t_zdau * 1e3 / 1e12},
-            "note": "algorithmic: TRPLU 6M+7S = 636 MAC32, 96 B in + 192 B out; ZDAU 9M+7S = 828 MAC32, 192 B in + 192 B out"}
+            "trplu": _po(t_trplu, 636, 288), "zdau": _po(t_zdau, 828, 384), "dblu": _po(t_dblu, 244, 288), "zaddu": _po(t_zaddu, 392, 384),
+            "add_z2_1": _po(t_addz, 592, 288),
+            "note": "algorithmic MAC32 / bytes per point: DBLU 1M+5S = 244 / 96+192; ZADDU 5M+2S = 392 / 192+192; TRPLU 6M+7S = 636 / 96+192; "
+                    "ZDAU 9M+7S = 828 / 192+192; ADD_Z2_1 7M+4S = 592 / 192+96"}
         del r2, J2, P2, Q2, R2, O2
         # BASELINE configs[3]: generator, 2^24 scalars (same ladder with P = G: the only form that keeps the reference's (X:Y:Z))
         n4 = 1 << 24
         k4 = dev.synth_values(dev.empty(n4, 1), SEED_SCALARS, 0, n4, 0)
         O4 = dev.empty(n4, 3)
+        dev.scalar_mult_base(O4, k4, n4); torch.cuda.synchronize()     # builds the fixed-base table (once per device)
         t_base = timed(lambda: dev.scalar_mult_base(O4, k4, n4), 1)
-        aux["scalar_mult_base_2^24"] = {"ms": t_base, "scalar_mults_per_s": n4 / t_base * 1e3, "frac_of_imad_peak": n4 * MAC32_PER_SCALAR_MULT / t_base * 1e3 / peak_wide}
+        t_base_plain = timed(lambda: dev.scalar_mult_base(O4, k4, n4, table=False), 1)
+        # with the table of 2^16 ladder states the kernel executes TRPLU + 15 ZDAU fewer per lane
+        mac_tab = MAC32_PER_SCALAR_MULT - 636 - 15 * 828
+        aux["scalar_mult_base_2^24"] = {"ms": t_base, "scalar_mults_per_s": n4 / t_base * 1e3,
+                                        "executed_mac32_per_lane": mac_tab, "frac_of_imad_peak": n4 * mac_tab / t_base * 1e3 / peak_wide,
+                                        "table": "2^16 ladder states of G (10 MiB, L2-resident), bit-exact",
+                                        "plain_ladder": {"ms": t_base_plain, "scalar_mults_per_s": n4 / t_base_plain * 1e3,
+                                                         "frac_of_imad_peak": n4 * MAC32_PER_SCALAR_MULT / t_base_plain * 1e3 / peak_wide}}
         del k4, O4
         del a, b, o1, flush
 

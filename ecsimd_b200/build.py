@@ -17,7 +17,7 @@ OBJDIR = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libecb200.so")
 
 SOURCES = ["kernels_field.cu", "kernels_point.cu", "kernels_generic.cu"]
-HEADERS = ["fp256.cuh", "fp256_mul_gen.cuh", "fpgen.cuh", "point.cuh", "layout.cuh", "host_common.cuh", os.path.join("..", "..", "include", "ecb200.h")]
+HEADERS = ["fp256.cuh", "fp256_mul_gen.cuh", "fpgen.cuh", "point.cuh", "zdau_order.inc", "layout.cuh", "host_common.cuh", os.path.join("..", "..", "include", "ecb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "550"]
 

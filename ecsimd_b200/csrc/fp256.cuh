@@ -84,7 +84,9 @@ static __device__ __noinline__ uint32_t fp_ge_p_rare(uint32_t t0, uint32_t t1, u
 //           in Exact mode if anything was recorded (the scalar-mult ladder: keeps branches and
 //           calls out of its hot loop).  `top` collects the largest pre-reduction top word seen
 //           (0xffffffff <=> the conditional subtraction may have been decided wrongly);
-//           `dirty` is set when a squaring operand is in the reference's lost-carry set.
+//           A squaring operand in the reference's lost-carry set is repaired in place in both modes
+//           (the exact test is already behind a rarely taken branch; `dirty` is kept for callers
+//           that want to force the exact re-run).
 struct Exact {};
 struct Lazy {
   uint32_t top = 0;
@@ -153,6 +155,31 @@ __device__ __forceinline__ fe fp_shl(const fe& a, M& mode) {
 }
 template <int COUNT>
 __device__ __forceinline__ fe fp_shl(const fe& a) { Exact e; return fp_shl<COUNT>(a, e); }
+
+// 4a mod p for a value that only feeds multiplications: any representative below 2^256 will do
+// there (fp_mul takes ANY 256-bit pattern and returns the canonical residue), so one pass replaces
+// two canonical doublings.  4a = s + t*2^256 with s = (a << 2) mod 2^256, t = a >> 254, and
+// 4a - t*p = s + t*(2^256 - p); t*(2^256 - p) = {t, 0, 0, -t, m, m, ~t & m, t + m}, m = -(t != 0).
+// The sum can pass 2^256 only if s >= 2^256 - 3*2^224: recorded in z.top like every other rare case.
+__device__ __forceinline__ fe fp_shl2_mulonly(const fe& a, Lazy& z) {
+  fe s;
+#pragma unroll
+  for (int i = 7; i > 0; i--) s.v[i] = __funnelshift_l(a.v[i - 1], a.v[i], 2);
+  s.v[0] = a.v[0] << 2;
+  const uint32_t t = a.v[7] >> 30;
+  const uint32_t nt = 0u - t;
+  const uint32_t m = (uint32_t)((int32_t)nt >> 31);
+  const uint32_t w6 = m & ~t, w7 = t + m;
+  z.top = max(z.top, s.v[7] | 3u);
+  fe r;
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, 0; addc.cc.u32 %2, %10, 0; addc.cc.u32 %3, %11, %17; "
+      "addc.cc.u32 %4, %12, %18; addc.cc.u32 %5, %13, %18; addc.cc.u32 %6, %14, %19; addc.u32 %7, %15, %20;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+        "r"(t), "r"(nt), "r"(m), "r"(w6), "r"(w7));
+  return r;
+}
+__device__ __forceinline__ fe fp_shl2_mulonly(const fe& a, Exact& e) { return fp_shl<2>(a, e); }
 
 template <class M>
 __device__ __forceinline__ fe fp_mul(const fe& a, const fe& b, M& mode) {
@@ -228,9 +255,21 @@ static __device__ __noinline__ void fp_sqr_quirk_slow(uint32_t* r, const uint32_
 
 // exact test: is some cross-product high word 0x7fffffff (INT_MAX as a signed int)?
 static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t* a) {
+  // straight-line: this runs for ~1 lane in 1 200 squarings (first-level false positives), i.e. in
+  // about one ladder step in six per warp, so its length matters a little
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = a[i];
   int m = 0;
-  for (int i = 0; i < 7; i++)
-    for (int j = i + 1; j < 8; j++) m = max(m, (int)__umulhi(a[i], a[j]));
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+#pragma unroll
+    for (int j = i + 1; j < 8; j += 2) {
+      const int h0 = (int)__umulhi(w[i], w[j]);
+      const int h1 = (j + 1 < 8) ? (int)__umulhi(w[i], w[j + 1]) : 0;
+      m = __vimax3_s32(m, h0, h1);
+    }
+  }
   return (uint32_t)m == 0x7fffffffu;
 }
 
@@ -309,16 +348,32 @@ __device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
   }
   return r;
 }
+// Cold path shared by the Lazy-mode squarings: for each of the n operands (8 words each) that
+// passes the exact test, overwrite its result with the reference's defective square.
+static __device__ __noinline__ uint32_t fp_quirk_fix(uint32_t* res, const uint32_t* ops, int n) {
+  uint32_t fixed = 0;
+  for (int k = 0; k < n; k++) {
+    if (fp_sqr_quirk_filter_exact(ops + 8 * k)) {
+      fp_sqr_quirk_slow(res + 8 * k, ops + 8 * k);
+      fixed |= 1u << k;
+    }
+  }
+  return fixed;
+}
+
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr(const fe& a, Lazy& mode) {
   uint32_t qx;
-  const fe r = fp_sqr_core<QUIRK>(a, mode, qx);
+  fe r = fp_sqr_core<QUIRK>(a, mode, qx);
   if (QUIRK) {
     if (__builtin_expect(fp_sqr_quirk_filter(a, qx) < 0x20000u, 0)) {
-      uint32_t in[8];
+      uint32_t in[8], out[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
-      if (fp_sqr_quirk_filter_exact(in)) mode.dirty = 1u;
+      if (fp_quirk_fix(out, in, 1)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = out[i];
+      }
     }
   }
   return r;
@@ -327,8 +382,10 @@ template <bool QUIRK = true>
 __device__ __forceinline__ fe fp_sqr(const fe& a) { Exact e; return fp_sqr<QUIRK>(a, e); }
 
 // Grouped form for the point formulas: fp_sqr_acc squares and only folds the first-level filter of
-// its operand into `fm`; fp_quirk_check then resolves a whole group of squarings with ONE branch.
-// Exact mode resolves each squaring in place (fm unused), so both modes share the formulas.
+// its operand into `fm`; fp_quirk_check then resolves a whole group of squarings with ONE branch,
+// repairing the results in place -- it must follow the group's squarings before any of their
+// results is used.  Exact mode resolves each squaring in place (fm unused), so both modes share the
+// formulas.
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr_acc(const fe& a, Exact& mode, uint32_t&) { return fp_sqr<QUIRK>(a, mode); }
 template <bool QUIRK>
@@ -338,34 +395,38 @@ __device__ __forceinline__ fe fp_sqr_acc(const fe& a, Lazy& mode, uint32_t& fm) 
   if (QUIRK) fm = fp_sqr_quirk_filter(a, qx, fm);
   return r;
 }
-static __device__ __noinline__ uint32_t fp_quirk_exact3(const uint32_t* a, int n) {
-  uint32_t hit = 0;
-  for (int k = 0; k < n; k++) hit |= fp_sqr_quirk_filter_exact(a + 8 * k);
-  return hit;
-}
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, const fe&) {}
+__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, fe&, const fe&, fe&) {}
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, const fe&, const fe&) {}
+__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, fe&, const fe&, fe&, const fe&, fe&) {}
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Lazy& mode, uint32_t fm, const fe& a, const fe& b) {
+__device__ __forceinline__ void fp_quirk_check(Lazy&, uint32_t fm, const fe& a, fe& ra, const fe& b, fe& rb) {
   if (QUIRK) {
     if (__builtin_expect(fm < 0x20000u, 0)) {
-      uint32_t in[16];
+      uint32_t in[16], out[16];
 #pragma unroll
-      for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; }
-      if (fp_quirk_exact3(in, 2)) mode.dirty = 1u;
+      for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; out[i] = ra.v[i]; out[8 + i] = rb.v[i]; }
+      if (fp_quirk_fix(out, in, 2)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { ra.v[i] = out[i]; rb.v[i] = out[8 + i]; }
+      }
     }
   }
 }
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Lazy& mode, uint32_t fm, const fe& a, const fe& b, const fe& c) {
+__device__ __forceinline__ void fp_quirk_check(Lazy&, uint32_t fm, const fe& a, fe& ra, const fe& b, fe& rb, const fe& c, fe& rc) {
   if (QUIRK) {
     if (__builtin_expect(fm < 0x20000u, 0)) {
-      uint32_t in[24];
+      uint32_t in[24], out[24];
 #pragma unroll
-      for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; in[16 + i] = c.v[i]; }
-      if (fp_quirk_exact3(in, 3)) mode.dirty = 1u;
+      for (int i = 0; i < 8; i++) {
+        in[i] = a.v[i]; in[8 + i] = b.v[i]; in[16 + i] = c.v[i];
+        out[i] = ra.v[i]; out[8 + i] = rb.v[i]; out[16 + i] = rc.v[i];
+      }
+      if (fp_quirk_fix(out, in, 3)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { ra.v[i] = out[i]; rb.v[i] = out[8 + i]; rc.v[i] = out[16 + i]; }
+      }
     }
   }
 }

@@ -60,8 +60,12 @@ __device__ __noinline__ void point_op_exact(void* out1, void* out2, const void* 
   point_store<OP>(out1, out2, n, i, r, w);
 }
 
+#ifndef ECB200_POINT_THREADS
+#define ECB200_POINT_THREADS 128
+#endif
+constexpr int kPointThreads = ECB200_POINT_THREADS;
 template <int OP, bool QUIRK>
-__global__ void __launch_bounds__(128) k_point(void* out1, void* out2, const void* A, const void* B, size_t n) {
+__global__ void __launch_bounds__(kPointThreads) k_point(void* out1, void* out2, const void* A, const void* B, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Lazy md;
@@ -276,9 +280,9 @@ static int point_call(void* out1, void* out2, const void* A, const void* B, size
   if (two_in && (rc = st.in(B, 3, &dB))) return rc;
   if ((rc = st.out(out1, 3, &d1))) return rc;
   if (two_out && (rc = st.out(out2, 3, &d2))) return rc;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
-  if (quirk_on(flags)) k_point<OP, true><<<blocks, 128, 0, st.s>>>(d1, d2, dA, dB, n);
-  else k_point<OP, false><<<blocks, 128, 0, st.s>>>(d1, d2, dA, dB, n);
+  const unsigned blocks = (unsigned)((n + kPointThreads - 1) / kPointThreads);
+  if (quirk_on(flags)) k_point<OP, true><<<blocks, kPointThreads, 0, st.s>>>(d1, d2, dA, dB, n);
+  else k_point<OP, false><<<blocks, kPointThreads, 0, st.s>>>(d1, d2, dA, dB, n);
   ECB_LAUNCH_CHECK();
   return st.finish();
 }
@@ -321,20 +325,26 @@ static int base_table(bool q, cudaStream_t s, const uint4** out) {
   return ECB200_OK;
 }
 
-template <bool Q, int L>
-static int launch_ladder_ql(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, cudaStream_t s, bool use_table) {
+// One launch for the whole batch, whatever its size: SMs do not run in step (a few are ~3 % slower
+// than the rest), so with dynamic block scheduling the fast ones simply take more blocks; splitting
+// a batch into "full waves + a tail launch" was measured and loses that slack at the kernel boundary
+// (2^20 lanes: 43.6 ms in one launch, 45.2 ms as 13 full waves + tail).
+template <bool Q, int MODE, int L, int TABW>
+static int launch_ladder_waves(void* dout, const void* dk, const void* dP, int k_bcast, size_t n, cudaStream_t s, const uint4* tab) {
   const unsigned blocks = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
-  if (mode == 0) {
-    k_scalar_mult_sync<Q, 0, kLadderThreads, L, 0><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, nullptr);
-  } else {
-    const uint4* tab = nullptr;
-    int rc = use_table ? base_table(Q, s, &tab) : ECB200_OK;
-    if (rc) return rc;
-    if (tab) k_scalar_mult_sync<Q, 1, kLadderThreads, L, kBaseTabW><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, tab);
-    else k_scalar_mult_sync<Q, 1, kLadderThreads, L, 0><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, nullptr);
-  }
+  k_scalar_mult_sync<Q, MODE, kLadderThreads, L, TABW><<<blocks, kLadderThreads, 0, s>>>(dout, dk, dP, n, k_bcast, tab);
   ECB_LAUNCH_CHECK();
   return ECB200_OK;
+}
+
+template <bool Q, int L>
+static int launch_ladder_ql(void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, cudaStream_t s, bool use_table) {
+  if (mode == 0) return launch_ladder_waves<Q, 0, L, 0>(dout, dk, dP, k_bcast, n, s, nullptr);
+  const uint4* tab = nullptr;
+  int rc = use_table ? base_table(Q, s, &tab) : ECB200_OK;
+  if (rc) return rc;
+  if (tab) return launch_ladder_waves<Q, 1, L, kBaseTabW>(dout, dk, dP, k_bcast, n, s, tab);
+  return launch_ladder_waves<Q, 1, L, 0>(dout, dk, dP, k_bcast, n, s, nullptr);
 }
 static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int mode, int k_bcast, size_t n, bool q, cudaStream_t s, bool use_table = true) {
   if (L == L_SOA) return q ? launch_ladder_ql<true, L_SOA>(dout, dk, dP, mode, k_bcast, n, s, use_table) : launch_ladder_ql<false, L_SOA>(dout, dk, dP, mode, k_bcast, n, s, use_table);

@@ -64,11 +64,11 @@ __device__ __forceinline__ jac pt_zaddu(jac& P, const jac& O, MD& md) {
 
 // ZDAU core on bare coordinates: (X1,Y1) <- 2*(X1,Y1) + (X2,Y2); (X2,Y2) <- the same
 // point (X2,Y2) re-scaled to the new common Z; Z <- new Z.
-#ifndef ECB200_ZDAU_GROUPS
-#define ECB200_ZDAU_GROUPS 0
-#endif
 #ifndef ECB200_ZDAU_ORDER
-#define ECB200_ZDAU_ORDER 1
+#define ECB200_ZDAU_ORDER 2
+#endif
+#ifndef ECB200_ZDAU_ORDER_FILE
+#define ECB200_ZDAU_ORDER_FILE "zdau_order.inc"
 #endif
 template <bool QUIRK, class MD, int MIDSYNC = 0>
 __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z, MD& md, int grp = 0) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   // Y3p = ((Y1-Y2) + (W1p-X3pc))^2 - Dp - C - 2*A1p        [(W1p - X3pc) = -e3]
   const fe Y3p = fp_sub(fp_sub(fp_sub(fp_sqr<QUIRK>(fp_sub(dy, e3), md), Dp), C), A2);
   // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once instead of each multiplicand
-  const fe C4 = fp_shl<2>(C, md);
+  const fe C4 = fp_shl2_mulonly(C, md);
   const fe W1 = fp_mul(X3pc, C4, md);
   const fe W2 = fp_mul(W1p, C4, md);
   const fe W12 = fp_add(W1, W2, md);
@@ -103,6 +103,8 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe Dc = fp_sqr<QUIRK>(yp, md);
   const fe X2n = fp_sub(Dc, W12);
   const fe Y2n = fp_sub(fp_mul(yp, fp_sub(W1, X2n), md), A1);
+#elif ECB200_ZDAU_ORDER == 2
+#include ECB200_ZDAU_ORDER_FILE
 #else
   // Same values, statement order chosen so that consecutive multiplications are independent
   // (ptxas then overlaps their carry chains), and the squarings grouped so that one branch
@@ -110,9 +112,9 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe dx = fp_sub(X1, X2);
   const fe dy = fp_sub(Y1, Y2);
   uint32_t f1 = 0xffffffffu;
-  const fe Cp = fp_sqr_acc<QUIRK>(dx, md, f1);
-  const fe Dp = fp_sqr_acc<QUIRK>(dy, md, f1);
-  fp_quirk_check<QUIRK>(md, f1, dx, dy);
+  fe Cp = fp_sqr_acc<QUIRK>(dx, md, f1);
+  fe Dp = fp_sqr_acc<QUIRK>(dy, md, f1);
+  fp_quirk_check<QUIRK>(md, f1, dx, Cp, dy, Dp);
   const fe W1p = fp_mul(X1, Cp, md);
   const fe W2p = fp_mul(X2, Cp, md);
   const fe A1p = fp_mul(Y1, fp_sub(W1p, W2p), md);
@@ -120,45 +122,25 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe e3 = fp_sub(X3pc, W1p);
   const fe de = fp_sub(dy, e3);                            // (Y1-Y2) + (W1p-X3pc), (W1p - X3pc) = -e3
   const fe xe = fp_add(dx, e3, md);                        // X1 - X2 + X3pc - W1p
-#if ECB200_ZDAU_GROUPS == 0
   uint32_t f2 = 0xffffffffu;
-  const fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
-  const fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
-  const fe s6 = fp_sqr_acc<QUIRK>(xe, md, f2);
-  fp_quirk_check<QUIRK>(md, f2, e3, de, xe);
-  const fe C4 = fp_shl<2>(C, md);                          // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once
+  fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
+  fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
+  fe s6 = fp_sqr_acc<QUIRK>(xe, md, f2);
+  fp_quirk_check<QUIRK>(md, f2, e3, C, de, s4, xe, s6);
+  const fe C4 = fp_shl2_mulonly(C, md);                          // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once
   const fe W1 = fp_mul(X3pc, C4, md);
   const fe W2 = fp_mul(W1p, C4, md);
   const fe Z3 = fp_mul(Z, fp_sub(fp_sub(s6, Cp), C), md);
   if (MIDSYNC) { if (grp == 1) asm volatile("bar.sync 0;" ::: "memory"); }
   const fe A2 = fp_shl1(A1p, md);
-  const fe Y3p = fp_sub(fp_sub(fp_sub(s4, Dp), C), A2);
+  // Y3p = s4 - Dp - C - 2*A1p, yp = Y3p + A2, ym = Y3p - A2: yp is the partial sum itself
+  const fe yp = fp_sub(fp_sub(s4, Dp), C);
+  const fe Y3p = fp_sub(yp, A2);
   const fe ym = fp_sub(Y3p, A2);
-  const fe yp = fp_add(Y3p, A2, md);
   uint32_t f3 = 0xffffffffu;
-  const fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
-  const fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
-  fp_quirk_check<QUIRK>(md, f3, ym, yp);
-#else
-  uint32_t f2 = 0xffffffffu;
-  const fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
-  const fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
-  fp_quirk_check<QUIRK>(md, f2, e3, de);
-  const fe C4 = fp_shl<2>(C, md);                          // W1 = 4*X3pc*C, W2 = 4*W1p*C: quadruple C once
-  const fe W1 = fp_mul(X3pc, C4, md);
-  const fe W2 = fp_mul(W1p, C4, md);
-  if (MIDSYNC) { if (grp == 1) asm volatile("bar.sync 0;" ::: "memory"); }
-  const fe A2 = fp_shl1(A1p, md);
-  const fe Y3p = fp_sub(fp_sub(fp_sub(s4, Dp), C), A2);
-  const fe ym = fp_sub(Y3p, A2);
-  const fe yp = fp_add(Y3p, A2, md);
-  uint32_t f3 = 0xffffffffu;
-  const fe s6 = fp_sqr_acc<QUIRK>(xe, md, f3);
-  const fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
-  const fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
-  fp_quirk_check<QUIRK>(md, f3, xe, ym, yp);
-  const fe Z3 = fp_mul(Z, fp_sub(fp_sub(s6, Cp), C), md);
-#endif
+  fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
+  fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
+  fp_quirk_check<QUIRK>(md, f3, ym, D, yp, Dc);
   const fe A1 = fp_mul(Y3p, fp_sub(W1, W2), md);
   const fe W12 = fp_add(W1, W2, md);
   const fe X3 = fp_sub(D, W12);

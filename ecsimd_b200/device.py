@@ -68,6 +68,18 @@ def trplu(outP, out3, P, n, layout="soa", quirk=True):
     capi.call("ecb200_trplu", outP.data_ptr(), out3.data_ptr(), P.data_ptr(), n, _flags(layout, quirk), _stream())
 
 
+def dblu(outP, out2, P, n, layout="soa", quirk=True):
+    capi.call("ecb200_dblu", outP.data_ptr(), out2.data_ptr(), P.data_ptr(), n, _flags(layout, quirk), _stream())
+
+
+def zaddu(outP, outR, P, O, n, layout="soa", quirk=True):
+    capi.call("ecb200_zaddu", outP.data_ptr(), outR.data_ptr(), P.data_ptr(), O.data_ptr(), n, _flags(layout, quirk), _stream())
+
+
+def add_z2_1(outR, A, B, n, layout="soa", quirk=True):
+    capi.call("ecb200_add_z2_1", outR.data_ptr(), A.data_ptr(), B.data_ptr(), n, _flags(layout, quirk), _stream())
+
+
 def zdau(outQ, outR, P, Q, n, layout="soa", quirk=True):
     capi.call("ecb200_zdau", outQ.data_ptr(), outR.data_ptr(), P.data_ptr(), Q.data_ptr(), n, _flags(layout, quirk), _stream())
 

@@ -132,7 +132,12 @@ int ecb200_trplu(void* outP, void* out3, const void* P, size_t n, uint32_t flags
  * P: n Jacobian points with Z == R (as produced by from_affine); out: n Jacobian
  * points, Montgomery form, the same (X:Y:Z) representative as the reference. */
 int ecb200_scalar_mult_p256(void* out, const void* k, const void* P, size_t n, uint32_t flags, void* stream);
-/* Same with P = the generator for every lane (curve_group::WJG(), curve_group.h:39-41). */
+/* Same with P = the generator for every lane (curve_group::WJG(), curve_group.h:39-41).
+ * The ladder is right-to-left, so its state after the steps for scalar bits 1..16 depends only on
+ * those bits: the library keeps the 2^16 states of G in a 10 MiB device table (built on first use,
+ * per device) and resumes the ladder at bit 17 -- the reference's Jacobian (X, Y, Z) bit for bit,
+ * 16.5 of 256 steps cheaper.  ECB200_NO_BASE_TABLE (or ECB200_BASE_TABLE=0 in the environment)
+ * runs the plain ladder. */
 int ecb200_scalar_mult_p256_base(void* out, const void* k, size_t n, uint32_t flags, void* stream);
 /* scalar_mult_1s: one scalar (8 x u32, host memory) for all lanes   curve_group.h:221-251 */
 int ecb200_scalar_mult_p256_1s(void* out, const uint32_t* k1, const void* P, size_t n, uint32_t flags, void* stream);
