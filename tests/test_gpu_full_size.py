@@ -68,3 +68,38 @@ def test_generator_2p24(eng, orc):
     # the fixed-base table (all 2^16 indices occur among 2^24 random scalars) against the plain ladder
     out3 = dev.scalar_mult_base(dev.empty(n, 3), k, n, table=False)
     assert torch.equal(out, out3)
+
+
+def test_config5_shards_fold_to_the_whole(eng, orc):
+    """BASELINE configs[4] on one GPU: the index range of a 2^23-lane variable-base batch (the share
+    of one GPU in the 2^26-lane, 8-GPU job) cut by shard.shard_range into 8 'ranks' that regenerate
+    their inputs from (seed, global index): every shard's output equals the same lanes of the
+    whole-batch run, the xor of the shard checksums is the checksum of the whole, and sampled lanes
+    match the oracle."""
+    import torch
+    from ecsimd_b200 import device as dev
+    from ecsimd_b200.shard import shard_range
+    n, world = 1 << 23, 8
+
+    def inputs(lo, m):
+        k = dev.synth_values(dev.empty(m, 1), 0xEC51D004, lo, m, 0)
+        r = dev.synth_values(dev.empty(m, 1), 0xEC51D003, lo, m, 0)
+        J = dev.scalar_mult_base(dev.empty(m, 3), r, m)
+        P = dev.from_affine(dev.empty(m, 3), dev.to_affine(dev.empty(m, 2), J, m), m)
+        return k, P
+
+    k, P = inputs(0, n)
+    whole = dev.scalar_mult(dev.empty(n, 3), k, P, n)
+    torch.cuda.synchronize()
+    total = np.zeros(8, np.uint32)
+    for rank in range(world):
+        lo, hi = shard_range(n, rank, world)
+        ks, Ps = inputs(lo, hi - lo)
+        assert torch.equal(ks, k[:, lo:hi]) and torch.equal(Ps, P[:, lo:hi])          # seeded regeneration
+        part = dev.scalar_mult(dev.empty(hi - lo, 3), ks, Ps, hi - lo)
+        torch.cuda.synchronize()
+        assert torch.equal(part, whole[:, lo:hi])
+        total ^= dev.checksum(part)
+    assert np.array_equal(total, dev.checksum(whole))
+    idx = np.concatenate([np.arange(0, 64), np.arange(n - 64, n), np.arange(0, n, 1048573)])
+    assert np.array_equal(_lanes(whole, idx, 3), orc.scalar_mult(_lanes(k, idx, 1), _lanes(P, idx, 3)))
