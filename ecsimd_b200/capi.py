@@ -105,6 +105,11 @@ def init(device=0):
     check(load().ecb200_init(device))
 
 
+def shutdown():
+    """release the staging pool and the fixed-base tables of the current device (rebuilt on demand)"""
+    check(load().ecb200_shutdown())
+
+
 def launch_count():
     return int(load().ecb200_launch_count())
 

@@ -450,6 +450,8 @@ static int bytes_call(void* vals, void* bytes, int ncoord, size_t n, uint32_t fl
   }
   return ECB200_OK;
 }
+namespace ecb200 { int release_base_tables(); }
+
 extern "C" {
 
 int ecb200_abi_version(void) { return ECB200_ABI_VERSION; }
@@ -482,6 +484,8 @@ int ecb200_shutdown(void) {
   int device = 0;
   ECB_CUDA(cudaGetDevice(&device));
   ECB_CUDA(cudaDeviceSynchronize());
+  int rc = ecb200::release_base_tables();
+  if (rc) return rc;
   cudaMemPool_t pool;
   ECB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   ECB_CUDA(cudaMemPoolTrimTo(pool, 0));

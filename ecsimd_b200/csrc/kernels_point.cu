@@ -302,17 +302,17 @@ struct BaseTable {
   uint4* tab[2] = {nullptr, nullptr};  // [quirk]
   int device = -1;
 };
+static std::mutex g_base_mu;
+static BaseTable g_base[16];
 static int base_table(bool q, cudaStream_t s, const uint4** out) {
-  static std::mutex mu;
-  static BaseTable bt[16];
   static const bool enabled = [] { const char* e = getenv("ECB200_BASE_TABLE"); return !(e && e[0] == '0'); }();
   *out = nullptr;
   if (!enabled) return ECB200_OK;
   int dev = 0;
   ECB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16) return ECB200_OK;
-  std::lock_guard<std::mutex> lock(mu);
-  BaseTable& b = bt[dev];
+  std::lock_guard<std::mutex> lock(g_base_mu);
+  BaseTable& b = g_base[dev];
   if (!b.tab[q]) {
     uint4* t = nullptr;
     ECB_CUDA(cudaMalloc(&t, ((size_t)1 << kBaseTabW) * 160));
@@ -324,6 +324,18 @@ static int base_table(bool q, cudaStream_t s, const uint4** out) {
     b.tab[q] = t;
   }
   *out = b.tab[q];
+  return ECB200_OK;
+}
+// ecb200_shutdown: give the current device's tables back (they are rebuilt on the next use)
+int release_base_tables() {
+  int dev = 0;
+  ECB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return ECB200_OK;
+  std::lock_guard<std::mutex> lock(g_base_mu);
+  for (auto& t : g_base[dev].tab) {
+    if (t) ECB_CUDA(cudaFree(t));
+    t = nullptr;
+  }
   return ECB200_OK;
 }
 

@@ -120,6 +120,15 @@ def test_scalar_mult_base_table(eng, orc):
     assert np.array_equal(eng.scalar_mult_base(k, quirk=False), eng.scalar_mult_base(k, quirk=False, table=False))
 
 
+def test_shutdown_releases_and_rebuilds_the_base_table(eng):
+    import ecsimd_b200
+    k = raw256(4242, 64)
+    a = eng.scalar_mult_base(k)
+    ecsimd_b200.shutdown()
+    assert np.array_equal(eng.scalar_mult_base(k), a)          # table rebuilt on demand
+    assert np.array_equal(eng.scalar_mult_base(k, table=False), a)
+
+
 @pytest.mark.parametrize("layout", ["pack4", "soa"])
 def test_scalar_mult_layouts(eng, orc, pts, layout):
     n = 64
