@@ -71,6 +71,26 @@ def test_scalar_mult_random_and_edge(eng, orc, pts):
     assert not got[0, 16:].any()
 
 
+def test_scalar_mult_any_bit_pattern(eng, orc):
+    """Out-of-contract points (arbitrary 256-bit patterns, top words all ones, values >= p): the
+    reference does no validation and returns deterministic garbage; so must the ladder.  These
+    inputs hit the 2^-32 cases of the fast conditional subtractions, i.e. they exercise the
+    flagged lanes' exact re-run (pt_scalar_mult_exact), which ordinary inputs never reach."""
+    n = 64
+    P = np.concatenate([raw256(71, 2 * n).reshape(n, 16), np.tile(to_words([_libs.R_INT % _libs.P_INT]), (n, 1))], axis=1)
+    P[:16, 7] = 0xFFFFFFFF                    # x with an all-ones top word (may or may not be < p)
+    P[16:32, 15] = 0xFFFFFFFF                 # same for y
+    P[32:40, :16] = 0xFFFFFFFF                # x = y = 2^256 - 1
+    P[40:44, :8] = to_words([_libs.P_INT])[0]   # x = p
+    P[44:48, 8:16] = to_words([_libs.P_INT - 1])[0]
+    k = raw256(72, n)
+    k[:8] = to_words(EDGE_SCALARS[:8])
+    want = orc.scalar_mult(k, P)
+    assert np.array_equal(eng.scalar_mult(k, P), want)
+    for layout, conv in (("pack4", (eng.lane_to_pack4, eng.pack4_to_lane)), ("soa", (eng.lane_to_soa, eng.soa_to_lane))):
+        assert np.array_equal(conv[1](eng.scalar_mult(conv[0](k, 1), conv[0](P, 3), layout=layout), 3), want)
+
+
 def test_scalar_mult_reference_kats(eng, orc):
     """tests/curve_group.cpp:117-173: k*G for k = 5, 0bc1b1f2...8827, 0a891cec...bd80 (affine KATs)"""
     G = np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)
