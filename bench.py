@@ -137,8 +137,28 @@ def cpu_reference_rate(seconds_target, cores):
     t = run(n0)
     n = max(n0, int(n0 * seconds_target / max(t, 1e-6)) // (4 * cores) * (4 * cores))
     t = run(n)
-    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d scalar mults (same seeded scalars, P=G), %.1f s, %d threads" % (n, t, cores)}, (lib, kind)
+    res = {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d scalar mults (same seeded scalars, P=G), %.1f s, %d threads" % (n, t, cores)}
+    # also one thread (ops/s/core), and the reference's mgry_mul for BASELINE configs[0]; ~2 s each
+    try:
+        lib1 = (_libs.reference(nt=1) if kind == "reference" else _libs.oracle(nt=1))
+        n1 = 4096
+        GJ = lib1.from_affine(np.repeat(G, n1, axis=0))
+        k1 = _libs.raw256(SEED_SCALARS, n1)
+        lib1.scalar_mult(k1[:64], GJ[:64])
+        t0 = time.perf_counter(); lib1.scalar_mult(k1, GJ); t1 = time.perf_counter() - t0
+        res["single_thread"] = {"value": n1 / t1, "unit": UNIT, "sample": "%d scalar mults, %.1f s" % (n1, t1)}
+        a, b = _libs.field_elems(0xEC51D001, 1 << 20), _libs.field_elems(0xEC51D002, 1 << 20)
+        lib.mgry_mul(a[:4096], b[:4096])
+        t0 = time.perf_counter()
+        for _ in range(8):
+            lib.mgry_mul(a, b)
+        tm = time.perf_counter() - t0
+        res["mulmod"] = {"value": 8 * (1 << 20) / tm, "unit": "mulmod/s", "cores": cores,
+                         "sample": "mgry_mul over 2^20 field elements x 8 (BASELINE configs[0]), %.2f s" % tm}
+    except Exception as ex:  # pragma: no cover
+        res["single_thread"] = {"error": repr(ex)}
+    return res, (lib, kind)
 
 
 def openssl_rate(cores, seconds=3.0):
