@@ -275,26 +275,30 @@ static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t
 
 // First-level filter.  Eight of the 28 cross products (ECB200_SQR_EXACT_PAIRS: every a_0*a_j and
 // a_1*a_7) are the first to land on their accumulator pair in fp_sqr_t9, so their exact high words
-// are there for free: qx = signed max of them, INT_MAX <=> hit.  The other 20 get a necessary
-// condition on the cheap 32-bit IMAD (2 clk/warp against 5 for IMAD.HI): with A = a_i >> 16,
-// B = a_j >> 16 we have A*B*2^32 <= a_i*a_j < (A*B + A + B + 1)*2^32, so hi32(a_i*a_j) == 0x7fffffff
-// forces A*B into [0x7ffe0000, 0x7fffffff], i.e. (A*B + 0x80020000) mod 2^32 < 0x20000.  An
-// unsigned 3-input min keeps it to one IMAD + half a VIMNMX3 per product.  The result m is
-// "< 0x20000 <=> maybe"; false-positive rate ~ 28 * 2^-15 per lane, resolved by the exact test
-// above; real hits (~6.5e-9 per lane) take the slow path.  `m` chains through several squarings.
-__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a, uint32_t qx, uint32_t m = 0xffffffffu) {
-  uint32_t h[8];
+// are there for free: fp_sqr_t9 folds them into qx (signed max, INT_MAX <=> hit).  The other 20 get
+// a necessary condition in fp32, one FFMA each: a hit needs a_i, a_j >= 2^31 and
+// a_i*a_j in [2^63 - 2^32, 2^63).  f(a) = as_float(0x3f000000 + (a >> 8)) is one LEA.HI; for a >= 2^31
+// it equals floor(a / 256) * 2^-23, i.e. a / 2^31 truncated to 24 bits, in [1, 2).  Then
+//     2 - 2^-30 - 3 * 2^-23  <  f_i * f_j  <=  a_i * a_j / 2^62  <  2
+// (x + y < 3 for x, y in [1, 2) with x*y < 2), so d = fma(-f_i, f_j, 2) -- one rounding of the exact
+// value -- lies in [0, 2^-21]: as an unsigned integer, bits(d) <= 0x35000000; negative d (product
+// above 2) has bits >= 0x80000000 and limbs below 2^31 can only add false positives.  An unsigned
+// 3-input min keeps it to one FFMA + half a VIMNMX3 per pair; `m` chains through a group of squarings.
+// False positives: ~2e-6 per square (the 16-bit integer form this replaces: 8.5e-4, i.e. a cold-path
+// excursion in one ladder step out of six per warp).
+#define ECB200_QF_THRESHOLD 0x35000000u
+__device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a, uint32_t m = 0xffffffffu) {
+  float f[8];
 #pragma unroll
-  for (int i = 1; i < 8; i++) h[i] = a.v[i] >> 16;
-  // 0x7fffffff - qx: 0 on an exact hit, >= 0x80000000 when qx is "negative", small only near INT_MAX
-  uint32_t pend = 0x7fffffffu - qx;
-  bool have = true;
+  for (int i = 1; i < 8; i++) f[i] = __uint_as_float((a.v[i] >> 8) + 0x3f000000u);
+  uint32_t pend = 0xffffffffu;
+  bool have = false;
 #pragma unroll
   for (int i = 1; i < 7; i++) {
 #pragma unroll
     for (int j = i + 1; j < 8; j++) {
       if (i == 1 && j == 7) continue;  // in qx
-      const uint32_t y = h[i] * h[j] + 0x80020000u;
+      const uint32_t y = __float_as_uint(__fmaf_rn(-f[i], f[j], 2.0f));
       if (have) { m = __vimin3_u32(m, pend, y); have = false; }
       else { pend = y; have = true; }
     }
@@ -302,6 +306,9 @@ __device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a, uint32_t qx
   if (have) m = min(m, pend);
   return m;
 }
+// hit test of a group: some approximate pair below the threshold, or some exact pair at INT_MAX
+__device__ __forceinline__ bool fp_quirk_maybe(uint32_t fm, uint32_t qx) { return fm <= ECB200_QF_THRESHOLD || qx == 0x7fffffffu; }
+#define ECB200_QX_INIT 0x80000000u  /* INT_MIN: neutral element of the signed max */
 // all 28 pairs through the IMAD condition (callers that do not run fp_sqr_t9: the generic-prime path)
 __device__ __forceinline__ uint32_t fp_sqr_quirk_filter_all(const fe& a) {
   uint32_t h[8];
@@ -332,10 +339,10 @@ __device__ __forceinline__ fe fp_sqr_core(const fe& a, M& mode, uint32_t& qx) {
 
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
-  uint32_t qx;
+  uint32_t qx = ECB200_QX_INIT;
   fe r = fp_sqr_core<QUIRK>(a, mode, qx);
   if (QUIRK) {
-    if (__builtin_expect(fp_sqr_quirk_filter(a, qx) < 0x20000u, 0)) {
+    if (__builtin_expect(fp_quirk_maybe(fp_sqr_quirk_filter(a), qx), 0)) {
       uint32_t in[8], out[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
@@ -348,6 +355,7 @@ __device__ __forceinline__ fe fp_sqr(const fe& a, Exact& mode) {
   }
   return r;
 }
+
 // Cold path shared by the Lazy-mode squarings: for each of the n operands (8 words each) that
 // passes the exact test, overwrite its result with the reference's defective square.
 static __device__ __noinline__ uint32_t fp_quirk_fix(uint32_t* res, const uint32_t* ops, int n) {
@@ -363,10 +371,10 @@ static __device__ __noinline__ uint32_t fp_quirk_fix(uint32_t* res, const uint32
 
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_sqr(const fe& a, Lazy& mode) {
-  uint32_t qx;
+  uint32_t qx = ECB200_QX_INIT;
   fe r = fp_sqr_core<QUIRK>(a, mode, qx);
   if (QUIRK) {
-    if (__builtin_expect(fp_sqr_quirk_filter(a, qx) < 0x20000u, 0)) {
+    if (__builtin_expect(fp_quirk_maybe(fp_sqr_quirk_filter(a), qx), 0)) {
       uint32_t in[8], out[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) in[i] = a.v[i];
@@ -382,27 +390,31 @@ template <bool QUIRK = true>
 __device__ __forceinline__ fe fp_sqr(const fe& a) { Exact e; return fp_sqr<QUIRK>(a, e); }
 
 // Grouped form for the point formulas: fp_sqr_acc squares and only folds the first-level filter of
-// its operand into `fm`; fp_quirk_check then resolves a whole group of squarings with ONE branch,
+// its operand into the group's accumulators (QuirkAcc: unsigned min of the fp32 test, signed max of
+// the exact high words); fp_quirk_check then resolves a whole group of squarings with ONE branch,
 // repairing the results in place -- it must follow the group's squarings before any of their
-// results is used.  Exact mode resolves each squaring in place (fm unused), so both modes share the
-// formulas.
+// results is used.  Exact mode resolves each squaring in place (accumulators unused), so both modes
+// share the formulas.
+struct QuirkAcc {
+  uint32_t fm = 0xffffffffu;
+  uint32_t qx = ECB200_QX_INIT;
+};
 template <bool QUIRK>
-__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Exact& mode, uint32_t&) { return fp_sqr<QUIRK>(a, mode); }
+__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Exact& mode, QuirkAcc&) { return fp_sqr<QUIRK>(a, mode); }
 template <bool QUIRK>
-__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Lazy& mode, uint32_t& fm) {
-  uint32_t qx;
-  const fe r = fp_sqr_core<QUIRK>(a, mode, qx);
-  if (QUIRK) fm = fp_sqr_quirk_filter(a, qx, fm);
+__device__ __forceinline__ fe fp_sqr_acc(const fe& a, Lazy& mode, QuirkAcc& q) {
+  const fe r = fp_sqr_core<QUIRK>(a, mode, q.qx);
+  if (QUIRK) q.fm = fp_sqr_quirk_filter(a, q.fm);
   return r;
 }
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, fe&, const fe&, fe&) {}
+__device__ __forceinline__ void fp_quirk_check(Exact&, const QuirkAcc&, const fe&, fe&, const fe&, fe&) {}
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Exact&, uint32_t, const fe&, fe&, const fe&, fe&, const fe&, fe&) {}
+__device__ __forceinline__ void fp_quirk_check(Exact&, const QuirkAcc&, const fe&, fe&, const fe&, fe&, const fe&, fe&) {}
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Lazy&, uint32_t fm, const fe& a, fe& ra, const fe& b, fe& rb) {
+__device__ __forceinline__ void fp_quirk_check(Lazy&, const QuirkAcc& q, const fe& a, fe& ra, const fe& b, fe& rb) {
   if (QUIRK) {
-    if (__builtin_expect(fm < 0x20000u, 0)) {
+    if (__builtin_expect(fp_quirk_maybe(q.fm, q.qx), 0)) {
       uint32_t in[16], out[16];
 #pragma unroll
       for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; out[i] = ra.v[i]; out[8 + i] = rb.v[i]; }
@@ -414,9 +426,9 @@ __device__ __forceinline__ void fp_quirk_check(Lazy&, uint32_t fm, const fe& a, 
   }
 }
 template <bool QUIRK>
-__device__ __forceinline__ void fp_quirk_check(Lazy&, uint32_t fm, const fe& a, fe& ra, const fe& b, fe& rb, const fe& c, fe& rc) {
+__device__ __forceinline__ void fp_quirk_check(Lazy&, const QuirkAcc& q, const fe& a, fe& ra, const fe& b, fe& rb, const fe& c, fe& rc) {
   if (QUIRK) {
-    if (__builtin_expect(fm < 0x20000u, 0)) {
+    if (__builtin_expect(fp_quirk_maybe(q.fm, q.qx), 0)) {
       uint32_t in[24], out[24];
 #pragma unroll
       for (int i = 0; i < 8; i++) {

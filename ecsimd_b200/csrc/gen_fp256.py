@@ -477,21 +477,20 @@ def gen_sqr():
     _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
     g = Emit()
     g.exact_pairs = []   # cross products whose high word is observed exactly (see fp_sqr_quirk_filter)
-    state = {"have": False}
 
     def hook(items):
-        # qx = signed max of the exact high words hi32(a_i*a_j): INT_MAX <=> that pair is in the
-        # reference's lost-carry set (fp256.cuh); three values per VIMNMX3
+        # qx = signed max of (its value on entry and) the exact high words hi32(a_i*a_j): INT_MAX <=>
+        # some pair is in the reference's lost-carry set (fp256.cuh).  qx is in/out so that a group
+        # of squarings shares one accumulator; two new values per VIMNMX3.
         regs = [r for (_, _, r) in items]
         g.exact_pairs.extend((i, j) for (i, j, _) in items)
         while regs:
-            take = regs[:2] if state["have"] else regs[:3]
-            regs = regs[len(take):]
-            args = (["qx"] if state["have"] else []) + take
+            take = regs[:2]
+            regs = regs[2:]
+            args = ["qx"] + take
             while len(args) < 3:
                 args.append(args[-1])
-            g.raw("qx = (uint32_t)__vimax3_s32((int)%s, (int)%s, (int)%s);" % tuple(args), ("max3s", "qx") + tuple(args), regs=["qx"])
-            state["have"] = True
+            g.raw("qx = (uint32_t)__vimax3_s32((int)%s, (int)%s, (int)%s);" % tuple(args), ("max3s", "qx") + tuple(args))
     touched = emit_products(g, SQR_E_CHAINS, SQR_O_CHAINS, "a%d", "a%d", {"e": None, "o": None}, fresh_hook=hook)
     # cross sum S = E + O: words 1..14, carry into word 15
     g.begin()
@@ -548,12 +547,13 @@ def check(g, unary=False, ntests=3000, seed=1):
         for k in range(8):
             env["a%d" % k] = (x >> (32 * k)) & M32
             env["b%d" % k] = (y >> (32 * k)) & M32
+        qx_in = env["qx"] = (0x80000000, 0x12345678, 0x7ffffffe)[(x ^ y) % 3]   # qx is in/out in the squaring
         simulate(g.ir, env)
         got = sum(env["h%d" % k] << (32 * k) for k in range(9))
         if unary and getattr(g, "exact_pairs", None):
             def sgn(v):
                 return v - 2**32 if v >= 2**31 else v
-            want_qx = max(sgn((env["a%d" % i] * env["a%d" % j]) >> 32) for (i, j) in g.exact_pairs) & M32
+            want_qx = max([sgn(qx_in)] + [sgn((env["a%d" % i] * env["a%d" % j]) >> 32) for (i, j) in g.exact_pairs]) & M32
             assert env["qx"] == want_qx, "qx mismatch"
         T = x * y
         m = (-T * pinv) % 2**256

@@ -111,7 +111,7 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   // resolves the squaring-defect filter of a whole group (fp_sqr_acc / fp_quirk_check).
   const fe dx = fp_sub(X1, X2);
   const fe dy = fp_sub(Y1, Y2);
-  uint32_t f1 = 0xffffffffu;
+  QuirkAcc f1;
   fe Cp = fp_sqr_acc<QUIRK>(dx, md, f1);
   fe Dp = fp_sqr_acc<QUIRK>(dy, md, f1);
   fp_quirk_check<QUIRK>(md, f1, dx, Cp, dy, Dp);
@@ -122,7 +122,7 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe e3 = fp_sub(X3pc, W1p);
   const fe de = fp_sub(dy, e3);                            // (Y1-Y2) + (W1p-X3pc), (W1p - X3pc) = -e3
   const fe xe = fp_add(dx, e3, md);                        // X1 - X2 + X3pc - W1p
-  uint32_t f2 = 0xffffffffu;
+  QuirkAcc f2;
   fe C = fp_sqr_acc<QUIRK>(e3, md, f2);
   fe s4 = fp_sqr_acc<QUIRK>(de, md, f2);
   fe s6 = fp_sqr_acc<QUIRK>(xe, md, f2);
@@ -137,7 +137,7 @@ __device__ __forceinline__ void pt_zdau_xy(fe& X1, fe& Y1, fe& X2, fe& Y2, fe& Z
   const fe yp = fp_sub(fp_sub(s4, Dp), C);
   const fe Y3p = fp_sub(yp, A2);
   const fe ym = fp_sub(Y3p, A2);
-  uint32_t f3 = 0xffffffffu;
+  QuirkAcc f3;
   fe D = fp_sqr_acc<QUIRK>(ym, md, f3);
   fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);
   fp_quirk_check<QUIRK>(md, f3, ym, D, yp, Dc);

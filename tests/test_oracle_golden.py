@@ -157,6 +157,35 @@ def test_quirk_filter_is_sound(orc):
     assert q.sum() > 1000 and not (q & ~hit).any()
 
 
+def _fp32_filter_bits(ai, aj):
+    """numpy model of the CUDA first-level filter (csrc/fp256.cuh, fp_sqr_quirk_filter):
+    f(a) = as_float(0x3f000000 + (a >> 8)); bits(fma(-f_i, f_j, 2.0f)).  f_i*f_j (48 significant bits)
+    and 2 - f_i*f_j are exact in float64, so one float64 -> float32 conversion is the fma's rounding."""
+    fi = ((ai >> np.uint64(8)).astype(np.uint32) + np.uint32(0x3F000000)).view(np.float32).astype(np.float64)
+    fj = ((aj >> np.uint64(8)).astype(np.uint32) + np.uint32(0x3F000000)).view(np.float32).astype(np.float64)
+    return (2.0 - fi * fj).astype(np.float32).view(np.uint32)
+
+
+def test_fp32_first_level_filter_is_sound():
+    """no false negative: every 32-bit pair whose product has high word 0x7fffffff passes the fp32 test
+    (bits <= 0x35000000), on pairs packed against both ends of every admissible product range"""
+    rnd = np.random.RandomState(12)
+    ai = (rnd.randint(0, 1 << 31, size=2_000_000).astype(np.uint64) | np.uint64(1 << 31))
+    ai[:64] = np.uint64(1 << 31); ai[64:128] = np.uint64(0xFFFFFFFF); ai[128:192] = np.uint64(0xB504F333)   # 2^31, 2^32-1, ~2^31.5
+    lo, hi = (np.uint64((1 << 63) - (1 << 32)) + ai - np.uint64(1)) // ai, np.uint64((1 << 63) - 1) // ai    # a_j range of a hit
+    ok = (lo <= hi) & (hi < np.uint64(1 << 32))
+    ai, lo, hi = ai[ok], lo[ok], hi[ok]
+    assert len(ai) > 1_000_000
+    for aj in (lo, hi):
+        assert (((ai * aj) >> np.uint64(32)) == np.uint64(0x7FFFFFFF)).all()
+        assert (_fp32_filter_bits(ai, aj) <= np.uint32(0x35000000)).all()
+        assert (_fp32_filter_bits(aj, ai) <= np.uint32(0x35000000)).all()
+    # and it is selective: random pairs almost never pass (the 16-bit integer form passed 3e-5 of them)
+    x = rnd.randint(0, 1 << 32, size=4_000_000, dtype=np.uint64)
+    y = rnd.randint(0, 1 << 32, size=4_000_000, dtype=np.uint64)
+    assert (_fp32_filter_bits(x, y) <= np.uint32(0x35000000)).mean() < 2e-6
+
+
 # ---- committed fixtures generated from the compiled reference -----------------------------------
 def _load(name):
     path = os.path.join(GOLDEN, name)

@@ -17,7 +17,7 @@ def _order_in_file():
     names = []
     for line in open(path):
         line = line.strip()
-        if not line or line.startswith("//") or line.startswith("uint32_t f1"):
+        if not line or line.startswith("//") or line.startswith("QuirkAcc f1"):
             continue
         m = re.match(r"(?:const )?fe (\w+) = ", line)
         if m:

@@ -21,7 +21,7 @@ else:
 cold = set()
 loop_ins = [(a, t) for a, t, _, _ in ins if lo <= a <= hi]
 for a, t in loop_ins:   # cold blocks: a forward predicated branch that jumps over a CALL
-    m = re.search(r"BRA\s+(0x[0-9a-f]+)", t)
+    m = re.search(r"BRA\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
     if m and t.startswith("@"):
         tgt = int(m.group(1), 16)
         if tgt > a and any("CALL" in t2 for a2, t2 in loop_ins if a < a2 < tgt):
