@@ -46,6 +46,7 @@ SYMBOLS = {
     "ecb200_scalar_mult_p256_1s": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_from_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
     "ecb200_to_affine": (_i, [_vp, _vp, _sz, _u32, _vp]),
+    "ecb200_scalar_mult_p256_affine": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_gen_mod_add": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_gen_mod_sub": (_i, [_vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "ecb200_gen_mod_shift_left_one": (_i, [_vp, _vp, _vp, _sz, _u32, _vp]),

@@ -541,4 +541,55 @@ int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* st
   return st.finish();
 }
 
+// scalar_mult(k, P).to_affine() in one call (what benchs/curve_group.cpp:28-46 of the reference times):
+// the Jacobian result stays on the device, so host callers move 128 B in and 64 B out per lane
+// instead of 128 + 96 and then 96 + 64.  Host batches are cut into the same two-wave chunks over
+// three streams as ecb200_scalar_mult_p256, each chunk running ladder -> to_affine -> copy out.
+static int scalar_mult_affine_call(void* out_xy, const void* k, const void* P, int mode, size_t n, uint32_t flags, void* stream) {
+  int rc = check_common(n, flags);
+  if (rc) return rc;
+  if (n == 0) return ECB200_OK;
+  if (!out_xy || !k || (mode == 0 && !P)) {
+    set_error("null pointer argument");
+    return ECB200_ERR_ARG;
+  }
+  cudaStream_t user = (cudaStream_t)stream;
+  if (on_device(flags)) {
+    Scratch sc(user);
+    void* J;
+    if ((rc = sc.alloc(&J, operand_bytes(n, 3)))) return rc;
+    if ((rc = scalar_mult_call(J, k, P, mode, 0, n, flags, stream))) return rc;
+    return ecb200_to_affine(out_xy, J, n, flags, stream);
+  }
+  const uint32_t dflags = (flags & ~ECB200_MEM_MASK) | ECB200_MEM_DEVICE;
+  const int L = layout_of(flags);
+  // LANE and PACK4 are contiguous per group of 4 lanes (a chunk is a byte range); SOA planes are not
+  const size_t chunk = (L == L_SOA) ? n : kChunkLanes;
+  cudaStream_t* ss = nullptr;
+  if ((rc = pipe_streams(&ss))) return rc;
+  ECB_CUDA(cudaStreamSynchronize(user));  // host buffers are the caller's: order after its pending work
+  size_t c = 0;
+  for (size_t lo = 0; lo < n; lo += chunk, c++) {
+    const size_t m = (n - lo < chunk) ? n - lo : chunk;
+    cudaStream_t s = ss[c % 3];
+    Scratch sc(s);
+    void *rk, *rP = nullptr, *rJ, *rxy;
+    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&rJ, operand_bytes(m, 3))) || (rc = sc.alloc(&rxy, operand_bytes(m, 2)))) return rc;
+    ECB_CUDA(cudaMemcpyAsync(rk, (const char*)k + lo * 32, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
+    if (mode == 0) {
+      if ((rc = sc.alloc(&rP, operand_bytes(m, 3)))) return rc;
+      ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
+    }
+    if ((rc = scalar_mult_call(rJ, rk, rP, mode, 0, m, dflags, s))) return rc;
+    if ((rc = ecb200_to_affine(rxy, rJ, m, dflags, s))) return rc;
+    ECB_CUDA(cudaMemcpyAsync((char*)out_xy + lo * 64, rxy, operand_bytes(m, 2), cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 3; i++) ECB_CUDA(cudaStreamSynchronize(ss[i]));
+  return ECB200_OK;
+}
+
+int ecb200_scalar_mult_p256_affine(void* out_xy, const void* k, const void* P, size_t n, uint32_t flags, void* stream) {
+  return scalar_mult_affine_call(out_xy, k, P, P ? 0 : 1, n, flags, stream);
+}
+
 }  // extern "C"

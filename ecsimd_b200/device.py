@@ -89,6 +89,11 @@ def to_affine(xy, J, n, layout="soa", quirk=True):
     return xy
 
 
+def scalar_mult_affine(xy, k, P, n, layout="soa", quirk=True):
+    capi.call("ecb200_scalar_mult_p256_affine", xy.data_ptr(), k.data_ptr(), None if P is None else P.data_ptr(), n, _flags(layout, quirk), _stream())
+    return xy
+
+
 def from_affine(J, xy, n, layout="soa"):
     capi.call("ecb200_from_affine", J.data_ptr(), xy.data_ptr(), n, _flags(layout), _stream())
     return J

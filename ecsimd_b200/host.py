@@ -138,6 +138,16 @@ def to_affine(J, layout="lane", quirk=True):
     return _run("ecb200_to_affine", [2], [J], 3, layout, quirk)
 
 
+def scalar_mult_affine(k, P=None, layout="lane", quirk=True, table=True):
+    """curve_group::scalar_mult(x, P).to_affine() in one call (benchs/curve_group.cpp:28-46); P=None: the generator"""
+    k = _in(k)
+    n = lanes_of(k, layout, 1)
+    out = np.zeros(_shape(layout, n, 2), np.uint32)
+    Pp = None if P is None else capi._p(_in(P))
+    capi.call("ecb200_scalar_mult_p256_affine", capi._p(out), capi._p(k), Pp, n, _flags(layout, quirk) | (0 if table else 0x200), None)
+    return out
+
+
 def from_x(x, layout="lane", quirk=True):
     """wide_curve_point::from_x: y = sqrt(x^3 - 3x + b)  curve_point_ops.h:12-22; -> (y, ok[n] uint8)"""
     x = _in(x)

@@ -148,6 +148,12 @@ int ecb200_scalar_mult_p256_1s(void* out, const uint32_t* k1, const void* P, siz
 int ecb200_from_affine(void* outJ, const void* xy, size_t n, uint32_t flags, void* stream);
 /* xy = J.to_affine()                                   jacobian_curve_point.h:33-42 */
 int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* stream);
+/* xy = scalar_mult(k, P).to_affine() in one call -- the pair of operations the reference's own bench
+ * times (benchs/curve_group.cpp:28-46, tests/curve_group.cpp:127-131); same values as
+ * ecb200_scalar_mult_p256 followed by ecb200_to_affine, but the Jacobian result never leaves the
+ * device (host callers move 128 B in and 64 B out per lane).  P == NULL: the generator for every
+ * lane (ecb200_scalar_mult_p256_base, with its table unless ECB200_NO_BASE_TABLE). */
+int ecb200_scalar_mult_p256_affine(void* xy, const void* k, const void* P, size_t n, uint32_t flags, void* stream);
 
 /* y = wide_curve_point::from_x(x).y(): point decompression, y = sqrt(x^3 - 3x + b) (classical x in,
  * classical y out)   curve_point_ops.h:12-22, curve_group.h:43-58, gfp.h:46-54.

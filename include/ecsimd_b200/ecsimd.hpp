@@ -227,6 +227,11 @@ struct curve_group<curve_nist_p256> {
   static void scalar_mult_base(WJCP* out, WBN const* x, std::size_t npacks) {
     detail::check(ecb200_scalar_mult_p256_base(out, x, 4 * npacks, detail::kHostPack, nullptr));
   }
+  // scalar_mult(x, P).to_affine() for npacks packs in one call (the pair benchs/curve_group.cpp:28-46 times);
+  // P == nullptr: the generator for every lane
+  static void scalar_mult_affine(WCP* out, WBN const* x, WJCP const* P, std::size_t npacks) {
+    detail::check(ecb200_scalar_mult_p256_affine(out, x, P, 4 * npacks, detail::kHostPack, nullptr));
+  }
   static void to_affine(WCP* out, WJCP const* J, std::size_t npacks) { detail::check(ecb200_to_affine(out, J, 4 * npacks, detail::kHostPack, nullptr)); }
   static void from_affine(WJCP* out, WCP const* a, std::size_t npacks) { detail::check(ecb200_from_affine(out, a, 4 * npacks, detail::kHostPack, nullptr)); }
 };

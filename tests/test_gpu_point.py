@@ -140,6 +140,30 @@ def test_scalar_mult_base_table(eng, orc):
     assert np.array_equal(eng.scalar_mult_base(k, quirk=False), eng.scalar_mult_base(k, quirk=False, table=False))
 
 
+def test_scalar_mult_affine_fused(eng, orc, pts):
+    """ecb200_scalar_mult_p256_affine == to_affine(scalar_mult(...)) == the reference, every layout, P and G"""
+    n = 64
+    k = raw256(91, n)
+    k[:8] = to_words(EDGE_SCALARS[:8])
+    P = pts[:n]
+    want = orc.to_affine(orc.scalar_mult(k, P))
+    assert np.array_equal(eng.scalar_mult_affine(k, P), want)
+    for layout, conv in (("pack4", (eng.lane_to_pack4, eng.pack4_to_lane)), ("soa", (eng.lane_to_soa, eng.soa_to_lane))):
+        assert np.array_equal(conv[1](eng.scalar_mult_affine(conv[0](k, 1), conv[0](P, 3), layout=layout), 2), want)
+    G = np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)
+    wantg = orc.to_affine(orc.scalar_mult(k, orc.from_affine(np.repeat(G, n, axis=0))))
+    assert np.array_equal(eng.scalar_mult_affine(k), wantg)
+    assert np.array_equal(eng.scalar_mult_affine(k, table=False), wantg)
+    # more lanes than one pipeline chunk (2 x 148 x 512): the chunked host path against the two-call path
+    m = 2 * 148 * 512 + 1000
+    km = raw256(92, m)
+    Pm = np.tile(P, (m // n + 1, 1))[:m]
+    two = eng.to_affine(eng.scalar_mult(km, Pm))
+    assert np.array_equal(eng.scalar_mult_affine(km, Pm), two)
+    idx = np.r_[0:16, m - 16:m]
+    assert np.array_equal(two[idx], orc.to_affine(orc.scalar_mult(km[idx], Pm[idx])))
+
+
 def test_shutdown_releases_and_rebuilds_the_base_table(eng):
     import ecsimd_b200
     k = raw256(4242, 64)
