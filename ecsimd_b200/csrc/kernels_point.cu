@@ -368,10 +368,10 @@ static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int 
   return ECB200_ERR_ARG;
 }
 
-// Host-memory batches are cut into chunks of two full waves (2 x 148 SMs x 512 lanes) that rotate
+// Host-memory batches are cut into chunks of one full wave (148 SMs x 512 lanes) that rotate
 // over three internal streams: the PCIe copies and layout conversions of one chunk overlap the
 // ladder kernel of another, and the partial last wave of a chunk overlaps the next chunk's blocks.
-constexpr size_t kChunkLanes = 2 * 148 * (size_t)kLadderThreads;
+constexpr size_t kChunkLanes = 148 * (size_t)kLadderThreads;
 struct PipeStreams {
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};
   int device = -1;
@@ -543,7 +543,7 @@ int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* st
 
 // scalar_mult(k, P).to_affine() in one call (what benchs/curve_group.cpp:28-46 of the reference times):
 // the Jacobian result stays on the device, so host callers move 128 B in and 64 B out per lane
-// instead of 128 + 96 and then 96 + 64.  Host batches are cut into the same two-wave chunks over
+// instead of 128 + 96 and then 96 + 64.  Host batches are cut into the same one-wave chunks over
 // three streams as ecb200_scalar_mult_p256, each chunk running ladder -> to_affine -> copy out.
 static int scalar_mult_affine_call(void* out_xy, const void* k, const void* P, int mode, size_t n, uint32_t flags, void* stream) {
   int rc = check_common(n, flags);

@@ -80,6 +80,11 @@ int main() {
     for (int i = 0; i < 64; i++) ks[i] = WBN{[&](int lane, int) { return bignum_256::from(uint64_t(4 * i + lane + 1)); }};
     CurveGroup::scalar_mult(out.data(), ks.data(), P.data(), 64);
     for (int i = 0; i < 64; i += 13) EXPECT_TRUE(out[i] == CurveGroup::scalar_mult(ks[i], P[i]));
+    // scalar_mult(...).to_affine() as one call (benchs/curve_group.cpp:28-35), on P and on the generator
+    std::vector<wide_curve_point<curve_nist_p256>> aff(64), affg(64);
+    CurveGroup::scalar_mult_affine(aff.data(), ks.data(), P.data(), 64);
+    CurveGroup::scalar_mult_affine(affg.data(), ks.data(), nullptr, 64);
+    for (int i = 0; i < 64; i += 13) { EXPECT_TRUE(aff[i] == out[i].to_affine()); EXPECT_TRUE(affg[i] == aff[i]); }
   }
   std::printf("ok %d\n", checks);
   return 0;
