@@ -43,8 +43,20 @@ def test_statements_match_the_search_tool():
     for n, t in osr.STMTS:
         want.add(t.replace("C4EXPR", "fp_shl2_mulonly(C, md)"))
         want.add(t.replace("C4EXPR", "fp_shl<2>(C, md)"))
+    # equivalent forms the tool may choose: commuted operands, the other association of a - b - c
+    want.update(osr.ALT.values())
+    want.update(t for _, t in osr.ALT_PARTNER.values())
     for l in body[1:]:
         assert l in want, l
+
+
+def test_double_subtractions_are_consistent():
+    """a - b - c may be associated either way, but both statements of the pair must agree"""
+    path = os.path.join(ROOT, "ecsimd_b200", "csrc", "zdau_order.inc")
+    body = {l.strip() for l in open(path)}
+    for first, (second, second_text) in osr.ALT_PARTNER.items():
+        assert (osr.ALT[first] in body) == (second_text in body), (first, second)
+        assert (osr.TEXT[first] in body) == (osr.TEXT[second] in body), (first, second)
 
 
 def test_dependencies_cover_the_repair_rule():

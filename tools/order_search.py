@@ -65,6 +65,27 @@ STMTS = [
     ("m9", "const fe m9 = fp_mul(yp, u2, md);"),
     ("Y2n", "const fe Y2n = fp_sub(m9, A1);"),
 ]
+# Equivalent forms of single statements (commutative operands, or the other association of a double
+# subtraction): same canonical values, different register pairing for ptxas.  A set of names selects the
+# alternative text.
+ALT = {
+    "W1p": "const fe W1p = fp_mul(Cp, X1, md);",
+    "W2p": "const fe W2p = fp_mul(Cp, X2, md);",
+    "A1p": "const fe A1p = fp_mul(dW, Y1, md);",
+    "W1": "const fe W1 = fp_mul(C4, X3pc, md);",
+    "W2": "const fe W2 = fp_mul(C4, W1p, md);",
+    "Z3": "const fe Z3 = fp_mul(z2, Z, md);",
+    "A1": "const fe A1 = fp_mul(dW2, Y3p, md);",
+    "m7": "const fe m7 = fp_mul(u1, ym, md);",
+    "m9": "const fe m9 = fp_mul(u2, yp, md);",
+    "xe": "const fe xe = fp_add(e3, dx, md);",
+    "W12": "const fe W12 = fp_add(W2, W1, md);",
+    "t1": "const fe t1 = fp_sub(Dp, W2p);",      # with X3pc = t1 - W1p
+    "z1": "const fe z1 = fp_sub(s6, C);",        # with z2 = z1 - Cp
+    "y1": "const fe y1 = fp_sub(s4, C);",        # with yp = y1 - Dp
+}
+ALT_PARTNER = {"t1": ("X3pc", "const fe X3pc = fp_sub(t1, W1p);"), "z1": ("z2", "const fe z2 = fp_sub(z1, Cp);"),
+               "y1": ("yp", "const fe yp = fp_sub(y1, Dp);")}
 NAMES = [n for n, _ in STMTS]
 TEXT = dict(STMTS)
 INPUTS = {"X1", "Y1", "X2", "Y2", "Z", "md", "QUIRK", "fe", "const", "fp_sub", "fp_add", "fp_mul", "fp_sqr_acc", "fp_quirk_check",
@@ -76,6 +97,9 @@ for n, t in STMTS:
     DEPS[n] = {i for i in ids if i in TEXT}
 # the filter words f1/f2/f3 are read-modify-write: squarings of a group before their check
 DEPS["C4"] |= {"C"}
+DEPS["t1"] |= {"W2p"}; DEPS["X3pc"] |= {"W1p"}      # union over both associations of Dp - W1p - W2p
+DEPS["z1"] |= {"C"}; DEPS["z2"] |= {"Cp"}
+DEPS["y1"] |= {"C"}; DEPS["yp"] |= {"Dp"}
 DEPS["chk1"] |= {"Cp", "Dp"}
 DEPS["chk2"] |= {"C", "s4", "s6"}
 DEPS["chk3"] |= {"D", "Dc"}
@@ -95,12 +119,14 @@ def valid(order):
     return True
 
 
-def emit(order, c4_lazy, path):
+def emit(order, c4_lazy, path, alts=frozenset()):
+    partner = {ALT_PARTNER[a][0]: ALT_PARTNER[a][1] for a in alts if a in ALT_PARTNER}
     with open(path, "w") as f:
         f.write("// generated by tools/order_search.py: statement order of the ZDAU step chosen against ptxas\n")
         f.write("  QuirkAcc f1, f2, f3;\n")
         for n in order:
-            t = TEXT[n].replace("C4EXPR", "fp_shl2_mulonly(C, md)" if c4_lazy else "fp_shl<2>(C, md)")
+            t = ALT[n] if n in alts else partner.get(n, TEXT[n])
+            t = t.replace("C4EXPR", "fp_shl2_mulonly(C, md)" if c4_lazy else "fp_shl<2>(C, md)")
             f.write("  " + t + "\n")
 
 
@@ -127,9 +153,9 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_ladder(void* __restrict__
 '''
 
 
-def evaluate(order, c4_lazy, tag):
+def evaluate(order, c4_lazy, tag, alts=frozenset()):
     inc = os.path.join(SCR, "order_%s.inc" % tag)
-    emit(order, c4_lazy, inc)
+    emit(order, c4_lazy, inc, alts)
     cu = os.path.join(SCR, "ladder_tu_%s.cu" % tag)
     with open(cu, "w") as f:
         f.write(TU)
@@ -175,20 +201,28 @@ def main():
     rnd = random.Random(seed)
     order = list(NAMES)
     c4 = False
-    if len(sys.argv) > 3:   # start from "lazy|canon name name ..."
+    alts = frozenset()
+    if len(sys.argv) > 3:   # start from "lazy|canon [alt=a,b,c] name name ..."
         toks = open(sys.argv[3]).read().split()
         c4 = toks[0] == "lazy"
-        order = toks[1:]
+        toks = toks[1:]
+        if toks and toks[0].startswith("alt="):
+            alts = frozenset(x for x in toks[0][4:].split(",") if x)
+            toks = toks[1:]
+        order = toks
         assert valid(order) and sorted(order) == sorted(NAMES)
-    best = evaluate(order, c4, tag)
+    best = evaluate(order, c4, tag, alts)
     print("start", best, flush=True)
     log = open(os.path.join(SCR, "order_search_%s.log" % tag), "a")
     for it in range(iters):
         cand = list(order)
-        cc4 = c4
+        cc4, calts = c4, alts
         r = rnd.random()
-        if r < 0.1:
+        if r < 0.05:
             cc4 = not c4
+        elif r < 0.5:
+            a = rnd.choice(sorted(ALT))
+            calts = alts ^ {a}
         else:
             # move one statement to another valid position (a few times)
             for _ in range(rnd.choice([1, 1, 2, 3])):
@@ -203,23 +237,23 @@ def main():
                     if valid(c2):
                         cand = c2
                         break
-        if cand == order and cc4 == c4:
+        if cand == order and cc4 == c4 and calts == alts:
             continue
         try:
-            sc = evaluate(cand, cc4, tag)
+            sc = evaluate(cand, cc4, tag, calts)
         except RuntimeError as e:
             print("compile error", str(e)[:300])
             continue
-        log.write("%d %r %r %s\n" % (it, sc, cc4, " ".join(cand)))
+        log.write("%d %r %r %s %s\n" % (it, sc, cc4, ",".join(sorted(calts)), " ".join(cand)))
         log.flush()
         if sc[0] <= best[0]:
             if sc[0] < best[0]:
-                print("iter %d: %.0f (n=%d mem=%d) c4_lazy=%s" % (it, sc[0], sc[1], sc[3], cc4), flush=True)
-            order, c4, best = cand, cc4, sc
-            emit(order, c4, os.path.join(SCR, "best_order_%s.inc" % tag))
+                print("iter %d: %.0f (n=%d mem=%d) c4_lazy=%s alts=%s" % (it, sc[0], sc[1], sc[3], cc4, ",".join(sorted(calts))), flush=True)
+            order, c4, alts, best = cand, cc4, calts, sc
+            emit(order, c4, os.path.join(SCR, "best_order_%s.inc" % tag), alts)
             with open(os.path.join(SCR, "best_order_%s.txt" % tag), "w") as f:
-                f.write(("lazy " if c4 else "canon ") + " ".join(order) + "\n")
-    print("best", best, c4, " ".join(order))
+                f.write(("lazy " if c4 else "canon ") + "alt=" + ",".join(sorted(alts)) + " " + " ".join(order) + "\n")
+    print("best", best, c4, sorted(alts), " ".join(order))
 
 
 if __name__ == "__main__":
