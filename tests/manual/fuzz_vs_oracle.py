@@ -4,7 +4,7 @@ points (a share of them out-of-contract bit patterns), all three layouts, variab
 affine.  usage: fuzz_vs_oracle.py [seeds] [lanes]"""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _libs
 import ecsimd_b200
