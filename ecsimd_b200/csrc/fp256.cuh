@@ -192,6 +192,81 @@ __device__ __forceinline__ fe fp_mul(const fe& a, const fe& b, M& mode) {
 }
 __device__ __forceinline__ fe fp_mul(const fe& a, const fe& b) { Exact e; return fp_mul(a, b, e); }
 
+// ---- a*b + c with one reduction ---------------------------------------------------------
+// fp_mul_wide: the unreduced 512-bit product.  fp_mul_acc(c, a, b) = (a*b + c) * R^-1 mod p, canonical:
+// the value mgry_add(mgry_mul(a, b), mgry_reduce(c)) of the reference, for one reduction instead of
+// two and no separate addition.  The quotient t = (a*b + c + m*p) / 2^256 is below 2^257 + p, i.e.
+// t = (k : s) with k in {0, 1, 2}, and t - k*p = s + k*(2^256 - p) is below 2^256 and canonical
+// unless s is within 2^226 of a multiple of 2^256 (k*(2^256 - p) = {k, 0, 0, -k, m, m, m & ~k, k + m},
+// m = -(k != 0)): the fast path is one 8-word add; the rare cases show as an all-ones top word before
+// or after it.
+struct fe512 {
+  uint32_t v[16];
+};
+__device__ __forceinline__ fe512 fp_mul_wide(const fe& a, const fe& b) {
+  fe512 t;
+  fp_mul512_words(t.v[0], t.v[1], t.v[2], t.v[3], t.v[4], t.v[5], t.v[6], t.v[7], t.v[8], t.v[9], t.v[10], t.v[11], t.v[12], t.v[13],
+                  t.v[14], t.v[15], a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
+                  b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6], b.v[7]);
+  return t;
+}
+__device__ __forceinline__ void fp_mul_acc_quot(fe& s, uint32_t& k, const fe512& c, const fe& a, const fe& b) {
+  fp_mul_acc_t9(s.v[0], s.v[1], s.v[2], s.v[3], s.v[4], s.v[5], s.v[6], s.v[7], k,
+                a.v[0], a.v[1], a.v[2], a.v[3], a.v[4], a.v[5], a.v[6], a.v[7],
+                b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], b.v[5], b.v[6], b.v[7],
+                c.v[0], c.v[1], c.v[2], c.v[3], c.v[4], c.v[5], c.v[6], c.v[7], c.v[8], c.v[9], c.v[10], c.v[11], c.v[12], c.v[13],
+                c.v[14], c.v[15]);
+}
+__device__ __forceinline__ fe fp_mul_acc(const fe512& c, const fe& a, const fe& b, Lazy& z) {
+  fe s;
+  uint32_t k;
+  fp_mul_acc_quot(s, k, c, a, b);
+  const uint32_t nk = 0u - k;
+  const uint32_t m = (uint32_t)((int32_t)nk >> 31);
+  const uint32_t w6 = m & ~k, w7 = k + m;
+  fe r;
+  asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, 0; addc.cc.u32 %2, %10, 0; addc.cc.u32 %3, %11, %17; "
+      "addc.cc.u32 %4, %12, %18; addc.cc.u32 %5, %13, %18; addc.cc.u32 %6, %14, %19; addc.u32 %7, %15, %20;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(s.v[0]), "r"(s.v[1]), "r"(s.v[2]), "r"(s.v[3]), "r"(s.v[4]), "r"(s.v[5]), "r"(s.v[6]), "r"(s.v[7]),
+        "r"(k), "r"(nk), "r"(m), "r"(w6), "r"(w7));
+  z.top = __vimax3_u32(z.top, s.v[7], r.v[7]);
+  return r;
+}
+// exact form (the flagged lanes' re-run): subtract p while the 258-bit value (k : s) is >= p
+static __device__ __noinline__ void fp_sub_p_while_ge(uint32_t* s, uint32_t k) {
+  const uint32_t pw[8] = ECB200_P_WORDS;
+  for (int it = 0; it < 3; it++) {
+    bool ge = k != 0u;
+    if (!ge) {
+      ge = true;  // s >= p ?
+      for (int i = 7; i >= 0; i--) {
+        if (s[i] != pw[i]) { ge = s[i] > pw[i]; break; }
+      }
+    }
+    if (!ge) return;
+    uint32_t borrow = 0;
+    for (int i = 0; i < 8; i++) {
+      const unsigned long long d = (unsigned long long)s[i] - pw[i] - borrow;
+      s[i] = (uint32_t)d;
+      borrow = (uint32_t)(d >> 63);
+    }
+    k -= borrow;
+  }
+}
+__device__ __forceinline__ fe fp_mul_acc(const fe512& c, const fe& a, const fe& b, Exact&) {
+  fe s;
+  uint32_t k;
+  fp_mul_acc_quot(s, k, c, a, b);
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = s.v[i];
+  fp_sub_p_while_ge(w, k);
+#pragma unroll
+  for (int i = 0; i < 8; i++) s.v[i] = w[i];
+  return s;
+}
+
 // ---- squaring ------------------------------------------------------------------------
 // The reference's square() (mul.h:160-212) accumulates the doubled cross products
 // `2*a_i*a_j + ret + prev` in wrap-around 64-bit lanes (mul.h:192-195); when that

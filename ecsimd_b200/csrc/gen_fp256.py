@@ -473,6 +473,31 @@ def gen_mul512():
     return g
 
 
+def gen_mul_acc():
+    """t = (a*b + c + m*p) / 2^256 for a 512-bit addend c (16 words c0..c15, any value): the product
+    chains as in gen_mul, the merge takes c as a second chain, the 17th word joins h8 (0..2).
+    Used to share one unreduced product between two results (point.cuh: Y3 and Y2n)."""
+    g = Emit()
+    touched = emit_products(g, MUL_E_CHAINS, MUL_O_CHAINS, "a%d", "b%d", {"e": 14, "o": None})
+    g.begin()
+    for w in range(1, 16):
+        ev = "e%d" % w if "e%d" % w in touched else 0
+        ov = "o%d" % w if "o%d" % w in touched else 0
+        g.add32("u%d" % w, ev, ov, w > 1, w < 15)
+    g.end()
+    g.begin()
+    g.add32("t0", "e0", "c0", False, True)
+    for w in range(1, 16):
+        g.add32("t%d" % w, "u%d" % w, "c%d" % w, True, True)
+    g.cap("t16", True)
+    g.end()
+    emit_reduction(g, ["t%d" % w for w in range(16)])
+    g.begin()
+    g.add32("h8", "h8", "t16", False, False)
+    g.end()
+    return g
+
+
 def gen_sqr():
     _check_cover(SQR_E_CHAINS, SQR_O_CHAINS, True)
     g = Emit()
@@ -593,18 +618,20 @@ __device__ __forceinline__ uint32_t ecb200_opaque_zero() { return g_ecb200_opaqu
 """
 
 
-def _emit_fn(name, g, nin, outs=None):
+def _emit_fn(name, g, nin, outs=None, extra_in=()):
     regs = set()
     for s in g.stmts:
         regs.update(s["rw"]); regs.update(s["wo"]); regs.update(s["ro"])
     outs = outs or ["h%d" % k for k in range(9)]
-    params = outs + ["a%d" % k for k in range(8)] + (["b%d" % k for k in range(8)] if nin == 2 else [])
+    params = outs + ["a%d" % k for k in range(8)] + (["b%d" % k for k in range(8)] if nin == 2 else []) + list(extra_in)
     local = sorted(regs - set(params), key=lambda x: (x.rstrip("0123456789"), int("0" + "".join(ch for ch in x if ch.isdigit()))))
     txt = "__device__ __forceinline__ void %s(\n" % name
     txt += "    " + ", ".join("uint32_t& %s" % o for o in outs) + ",\n"
     txt += "    " + ", ".join("uint32_t a%d" % k for k in range(8))
     if nin == 2:
         txt += ",\n    " + ", ".join("uint32_t b%d" % k for k in range(8))
+    if extra_in:
+        txt += ",\n    " + ", ".join("uint32_t %s" % n for n in extra_in)
     txt += ") {\n"
     txt += "  uint32_t " + ", ".join(local) + ";\n"
     txt += g.cxx() + "\n}\n\n"
@@ -616,6 +643,20 @@ def emit_header(path):
     nm = check(gm, unary=False)
     ns = check(gs, unary=True)
     g5 = gen_mul512()
+    ga = gen_mul_acc()
+    pinv = pow(P, -1, 2**256)
+    for x, y in _cases(1500, 7, False):
+        for c in (0, x * y ^ (x << 200), 2**512 - 1, (P - 1) * (P - 1), (x * x) % 2**512):
+            env = {}
+            for k in range(8):
+                env["a%d" % k] = (x >> (32 * k)) & M32
+                env["b%d" % k] = (y >> (32 * k)) & M32
+            for k in range(16):
+                env["c%d" % k] = (c >> (32 * k)) & M32
+            simulate(ga.ir, env)
+            T = x * y + c
+            m = (-T * pinv) % 2**256
+            assert sum(env["h%d" % k] << (32 * k) for k in range(9)) == (T + m * P) >> 256, "mul_acc mismatch"
     rnd = random.Random(5)
     for x, y in _cases(500, 5, False):
         env = {}
@@ -627,6 +668,8 @@ def emit_header(path):
     txt = (HEADER + _emit_fn("fp_mul_t9", gm, 2) + _emit_fn("fp_sqr_t9", gs, 1, outs=["h%d" % k for k in range(9)] + ["qx"]) +
            "// cross products (i, j) whose exact high word enters qx above\n" +
            "#define ECB200_SQR_EXACT_PAIRS {%s}\n\n" % ", ".join("{%d, %d}" % ij for ij in gs.exact_pairs) +
+           "// t = (a*b + c + m*p) / 2^256 with a 512-bit addend c; h8 in {0, 1, 2}\n" +
+           _emit_fn("fp_mul_acc_t9", ga, 2, extra_in=["c%d" % k for k in range(16)]) +
            "// T = a*b, the exact 512-bit product (mul.h:150-158), 16 words\n" +
            _emit_fn("fp_mul512_words", g5, 2, outs=["t%d" % k for k in range(16)]) + "}  // namespace ecb200\n")
     with open(path, "w") as f:

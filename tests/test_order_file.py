@@ -19,7 +19,7 @@ def _order_in_file():
         line = line.strip()
         if not line or line.startswith("//") or line.startswith("QuirkAcc f1"):
             continue
-        m = re.match(r"(?:const )?fe (\w+) = ", line)
+        m = re.match(r"(?:const )?fe(?:512)? (\w+) = ", line)
         if m:
             names.append(m.group(1))
             continue

@@ -53,17 +53,17 @@ STMTS = [
     ("D", "fe D = fp_sqr_acc<QUIRK>(ym, md, f3);"),
     ("Dc", "fe Dc = fp_sqr_acc<QUIRK>(yp, md, f3);"),
     ("chk3", "fp_quirk_check<QUIRK>(md, f3, ym, D, yp, Dc);"),
-    ("dW2", "const fe dW2 = fp_sub(W1, W2);"),
-    ("A1", "const fe A1 = fp_mul(Y3p, dW2, md);"),
+    # Y3 = ym*(W1 - X3) - Y3p*(W1 - W2) and Y2n = yp*(W1 - X2n) - Y3p*(W1 - W2) as (a*b + c) with ONE reduction each,
+    # sharing the unreduced product TA = Y3p*(W2 - W1)  (fp_mul_wide / fp_mul_acc, fp256.cuh)
+    ("dW2n", "const fe dW2n = fp_sub(W2, W1);"),
+    ("TA", "const fe512 TA = fp_mul_wide(Y3p, dW2n);"),
     ("W12", "const fe W12 = fp_add(W1, W2, md);"),
     ("X3", "const fe X3 = fp_sub(D, W12);"),
     ("u1", "const fe u1 = fp_sub(W1, X3);"),
-    ("m7", "const fe m7 = fp_mul(ym, u1, md);"),
-    ("Y3", "const fe Y3 = fp_sub(m7, A1);"),
+    ("Y3", "const fe Y3 = fp_mul_acc(TA, ym, u1, md);"),
     ("X2n", "const fe X2n = fp_sub(Dc, W12);"),
     ("u2", "const fe u2 = fp_sub(W1, X2n);"),
-    ("m9", "const fe m9 = fp_mul(yp, u2, md);"),
-    ("Y2n", "const fe Y2n = fp_sub(m9, A1);"),
+    ("Y2n", "const fe Y2n = fp_mul_acc(TA, yp, u2, md);"),
 ]
 # Equivalent forms of single statements (commutative operands, or the other association of a double
 # subtraction): same canonical values, different register pairing for ptxas.  A set of names selects the
@@ -75,9 +75,9 @@ ALT = {
     "W1": "const fe W1 = fp_mul(C4, X3pc, md);",
     "W2": "const fe W2 = fp_mul(C4, W1p, md);",
     "Z3": "const fe Z3 = fp_mul(z2, Z, md);",
-    "A1": "const fe A1 = fp_mul(dW2, Y3p, md);",
-    "m7": "const fe m7 = fp_mul(u1, ym, md);",
-    "m9": "const fe m9 = fp_mul(u2, yp, md);",
+    "TA": "const fe512 TA = fp_mul_wide(dW2n, Y3p);",
+    "Y3": "const fe Y3 = fp_mul_acc(TA, u1, ym, md);",
+    "Y2n": "const fe Y2n = fp_mul_acc(TA, u2, yp, md);",
     "xe": "const fe xe = fp_add(e3, dx, md);",
     "W12": "const fe W12 = fp_add(W2, W1, md);",
     "t1": "const fe t1 = fp_sub(Dp, W2p);",      # with X3pc = t1 - W1p
@@ -89,7 +89,7 @@ ALT_PARTNER = {"t1": ("X3pc", "const fe X3pc = fp_sub(t1, W1p);"), "z1": ("z2", 
 NAMES = [n for n, _ in STMTS]
 TEXT = dict(STMTS)
 INPUTS = {"X1", "Y1", "X2", "Y2", "Z", "md", "QUIRK", "fe", "const", "fp_sub", "fp_add", "fp_mul", "fp_sqr_acc", "fp_quirk_check",
-          "fp_shl1", "f1", "f2", "f3", "C4EXPR"}
+          "fp_shl1", "f1", "f2", "f3", "C4EXPR", "fe512", "fp_mul_wide", "fp_mul_acc"}
 DEPS = {}
 for n, t in STMTS:
     rhs = t.split("=", 1)[1] if n not in ("chk1", "chk2", "chk3") else t
