@@ -269,8 +269,9 @@ __device__ __forceinline__ jac pt_scalar_mult_mode(const Src& src, MD& md) {
   return out;
 }
 
-// The exact re-run for lanes the fast ladder flagged (a handful per million): same ladder, every
-// rare case resolved in place.  Kept out of line so that it costs the hot path nothing.
+// The exact re-run for lanes the fast ladder flagged (only the 2^-32 cases of the conditional
+// subtractions, now that defect squares are repaired in place): same ladder, every rare case
+// resolved in place.  Kept out of line so that it costs the hot path nothing.
 template <bool QUIRK>
 __device__ __noinline__ void pt_scalar_mult_exact(uint32_t* out24, const uint32_t* k8, const uint32_t* xy16) {
   Exact md;
