@@ -16,6 +16,11 @@ independent, each rank owns an index range, no collective on the data path).
            lane = 2299 mul x 64 + 1789 sqr x 36) / CUDA-event kernel time, against
            the IMAD.WIDE.U32 issue rate measured live on this GPU (ecb200_microbench)
 `cpu_baseline` the reference's own AVX2 code (oracle/_ref) on the box's host cores, bounded sample
+`aux.strong_2^26` BASELINE configs[4] as written: 2^26 (k,P) pairs cut over the N ranks by index range
+
+Multi-GPU runs (torchrun, one rank per GPU) exchange a few host scalars over gloo; no NCCL communicator
+is created: the path has no collective (ecsimd_b200/shard.py).  Every rank checks a sample of ITS OWN
+lanes against the CPU oracle; the run fails (exit code 1) if any rank disagrees.
 """
 import argparse
 import json
@@ -28,10 +33,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's banner (printed to stdout when NCCL_DEBUG is set,
-# as it is on the GPU boxes) out of it
-os.environ.pop("NCCL_DEBUG", None)
-os.environ["NCCL_DEBUG_FILE"] = os.devnull
 
 LANES_PER_GPU = 1 << 20
 MAC32_PER_SCALAR_MULT = 2299 * 64 + 1789 * 36   # 211 540
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=LANES_PER_GPU, help="lanes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 2^26-lane strong-scaling pass (aux.strong_2^26)")
+    ap.add_argument("--strong-log2", type=int, default=26)
     return ap.parse_args()
 
 
@@ -174,7 +177,9 @@ def openssl_rate(cores, seconds=3.0):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, on the
+    SAME workload as the GPU arm: every step runs scalar_mult over all 2^20 seeded (k, P) pairs (seeds
+    SEED_SCALARS / SEED_POINTS, P_i = r_i * G) with all host threads (~12 s per step on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -186,14 +191,9 @@ def run_reference_arm(args):
     kind = "reference"
     if lib is None:
         lib, kind = _libs.oracle(nt=cores), "port"
+    n = args.lanes
     G = np.concatenate([_libs.to_words([_libs.GX_INT]), _libs.to_words([_libs.GY_INT])], axis=1)
-    # bounded sample per step: ~2 s of CPU work
-    n0 = 256 * cores
-    GJ = lib.from_affine(np.repeat(G, n0, axis=0))
-    k = _libs.raw256(SEED_SCALARS, n0)
-    lib.scalar_mult(k, GJ)
-    t0 = time.perf_counter(); lib.scalar_mult(k, GJ); t = time.perf_counter() - t0
-    n = max(n0, int(n0 * 2.0 / max(t, 1e-6)) // (4 * cores) * (4 * cores))
+    # the GPU arm's inputs: P_i = r_i * G (r from SEED_POINTS), Montgomery (X, Y), Z = R; k from SEED_SCALARS
     P = lib.from_affine(lib.to_affine(lib.scalar_mult(_libs.raw256(SEED_POINTS, n), lib.from_affine(np.repeat(G, n, axis=0)))))
     k = _libs.raw256(SEED_SCALARS, n)
     for _ in range(args.warmup):
@@ -203,17 +203,62 @@ def run_reference_arm(args):
         lib.scalar_mult(k, P)
     el = time.perf_counter() - t0
     value = n * args.steps / el
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d scalar mults per step x %d steps (the full batch), %d threads" % (n, args.steps, cores)}
+    try:   # one thread (ops/s/core) and the p256_ref bench's OpenSSL arm, a few seconds each
+        lib1 = _libs.reference(nt=1) if kind == "reference" else _libs.oracle(nt=1)
+        n1 = 4096
+        t0 = time.perf_counter(); lib1.scalar_mult(k[:n1], P[:n1]); t1 = time.perf_counter() - t0
+        cpu["single_thread"] = {"value": n1 / t1, "unit": UNIT, "sample": "%d scalar mults, %.1f s" % (n1, t1)}
+    except Exception as ex:  # pragma: no cover
+        cpu["single_thread"] = {"error": repr(ex)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 limbs (u64 AVX2 lanes on the CPU)", "data": "synthetic",
-            "config": {"workload": "scalar_mult_p256 variable-base, bounded sample of %d (k,P) pairs per step on host cores" % n,
-                       "lanes_per_step": n},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "%d scalar mults per step x %d steps, %d threads" % (n, args.steps, cores)},
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": _config(n),
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "dtype: the reference computes on u32 digits held in u64 AVX2 lanes (mul.h:56-113); same (k,P) pairs as the GPU arm"}
+    p256 = openssl_rate(cores)
+    if p256:
+        line["p256_ref_openssl"] = p256
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _config(n):
+    """the `config` object both arms print (the driver compares them)"""
+    return {"workload": "scalar_mult_p256 variable-base, 2^%d (k,P) pairs per GPU per step (BASELINE configs[2])" % (n.bit_length() - 1),
+            "lanes_per_gpu": n, "layout": "SOA planes in HBM", "parallelism": "index-range shards, no collective",
+            "l2": "inputs+outputs per step = %d MiB > 126 MB L2" % (n * 224 >> 20), "quirk_exact": True}
+
+
+def _sample_idx(n, count=256):
+    """lanes a rank checks against the oracle: the first, the last and a strided sample of its range"""
+    import numpy as np
+    c = min(count, n)
+    idx = np.unique(np.concatenate([np.arange(min(c // 2, n)), np.arange(max(0, n - c // 2), n),
+                                    np.linspace(0, n - 1, num=c, dtype=np.int64)]))
+    return idx
+
+
+def spot_check(orc, k, P, out, lo, n, seed_scalars):
+    """this rank's sampled lanes of `out` against oracle.scalar_mult on the same inputs (checker only).
+    k, P, out: device SOA tensors of this rank; lo: global index of lane 0.  -> (ok, lanes checked)"""
+    import numpy as np
+    import torch
+    from ecsimd_b200 import host
+    import _libs
+    idx = _sample_idx(n)
+    ti = torch.from_numpy(idx).to(k.device)
+    kk = host.soa_to_lane(k.index_select(1, ti).contiguous().cpu().numpy().view(np.uint32), 1)
+    PP = host.soa_to_lane(P.index_select(1, ti).contiguous().cpu().numpy().view(np.uint32), 3)
+    got = host.soa_to_lane(out.index_select(1, ti).contiguous().cpu().numpy().view(np.uint32), 3)
+    # the device-generated scalars are the seeded ones the reference arm uses
+    first = _libs.raw256(seed_scalars, min(64, n), start=lo)
+    ok = np.array_equal(kk[:first.shape[0]], first) and np.array_equal(got, orc.scalar_mult(kk, PP))
+    return bool(ok), int(idx.size)
 
 
 def main():
@@ -269,27 +314,31 @@ def main():
     clocks = sampler.stop()
     shard.barrier()
     ms_local = e0.elapsed_time(e1)
-    ms = shard.max_over_ranks(ms_local, cuda if world > 1 else None)
-    lanes_total = shard.sum_over_ranks(n, cuda if world > 1 else None)
+    ms = shard.max_over_ranks(ms_local)
+    lanes_total = shard.sum_over_ranks(n)
     value = lanes_total * args.steps / (ms * 1e-3)
     kernel_ms = ms_local / args.steps                      # one ladder kernel launch per step on this path
     achieved = n * MAC32_PER_SCALAR_MULT / (kernel_ms * 1e-3)
 
-    # ---- parity spot check against the CPU oracle (checker only; not timed) -------------------------
-    parity = "skipped"
-    if rank == 0:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import _libs
-            orc = _libs.oracle(nt=os.cpu_count() or 1)
-            m = 512
-            kk = host.soa_to_lane(k[:, :m].contiguous().cpu().numpy().view(np.uint32), 1)
-            PP = host.soa_to_lane(P[:, :m].contiguous().cpu().numpy().view(np.uint32), 3)
-            got = host.soa_to_lane(out[:, :m].contiguous().cpu().numpy().view(np.uint32), 3)
-            assert np.array_equal(kk, _libs.raw256(SEED_SCALARS, m, start=lo))
-            parity = "ok" if np.array_equal(got, orc.scalar_mult(kk, PP)) else "MISMATCH"
-        except Exception as ex:  # pragma: no cover
-            parity = "error: %r" % (ex,)
+    # ---- parity: EVERY rank checks a sample of its own lanes against the CPU oracle, and that a second
+    # run reproduces its output bit for bit (checker only; not timed); the verdict is the min over ranks
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _libs
+    orc = _libs.oracle(nt=max(1, (os.cpu_count() or 1) // max(1, world)))
+    parity_ok, parity_note = False, ""
+    try:
+        ok_lanes, checked = spot_check(orc, k, P, out, lo, n, SEED_SCALARS)
+        sum1 = dev.checksum(out)
+        out.zero_()
+        step()
+        torch.cuda.synchronize()
+        ok_repeat = bool(np.array_equal(sum1, dev.checksum(out)))
+        parity_ok = ok_lanes and ok_repeat
+        parity_note = "%d lanes/rank vs oracle + repeat checksum" % checked
+    except Exception as ex:  # pragma: no cover
+        parity_note = "error on rank %d: %r" % (rank, ex)
+    parity_all = shard.min_over_ranks(1.0 if parity_ok else 0.0) == 1.0
+    parity = ("ok (%d rank%s; %s)" % (world, "" if world == 1 else "s", parity_note)) if parity_all else ("MISMATCH (%s)" % parity_note)
 
     # ---- end to end through the C ABI with host buffers (reference pack layout) ---------------------
     e2e_steps = max(1, min(args.steps, 4))
@@ -308,15 +357,66 @@ def main():
     for _ in range(e2e_steps):
         hcall()                                              # synchronous: returns when hout is written
     torch.cuda.synchronize()
-    e2e_s = shard.max_over_ranks(time.perf_counter() - t0, cuda if world > 1 else None)
+    e2e_s = shard.max_over_ranks(time.perf_counter() - t0)
     e2e_value = lanes_total * e2e_steps / e2e_s
-    e2e_ok = None
-    if rank == 0 and parity == "ok":
-        got = host.pack4_to_lane(hout[:128].numpy().view(np.uint32), 3)
-        e2e_ok = bool(np.array_equal(got, host.soa_to_lane(out[:, :512].contiguous().cpu().numpy().view(np.uint32), 3)))
+    # the host path returns what the device path computed: all lanes of this rank, every rank
+    got = host.pack4_to_lane(hout.numpy().view(np.uint32), 3)
+    e2e_ok = bool(np.array_equal(got, host.soa_to_lane(out.cpu().numpy().view(np.uint32), 3)))
+    e2e_ok = shard.min_over_ranks(1.0 if e2e_ok else 0.0) == 1.0
+    # the same call on PAGEABLE host memory (plain numpy arrays: what a std::vector of reference packs is)
+    pk, pP, pout = np.array(hk.numpy()), np.array(hP.numpy()), np.empty_like(hout.numpy())
+    pcall = lambda: capi.call("ecb200_scalar_mult_p256", capi._p(pout), capi._p(pk), capi._p(pP), n, flags_host, None)
+    pcall()
+    shard.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pcall()
+    e2e_pageable_s = shard.max_over_ranks(time.perf_counter() - t0)
+    e2e_pageable = {"value": lanes_total * e2e_steps / e2e_pageable_s, "unit": UNIT, "steps": e2e_steps,
+                    "matches_pinned": bool(shard.min_over_ranks(1.0 if np.array_equal(pout, hout.numpy()) else 0.0) == 1.0),
+                    "note": "numpy (pageable) pack4 buffers, staged through the library's pinned bounce buffers"}
+    del pk, pP, pout
+
+    # ---- BASELINE configs[4] as written: 2^26 (k,P) pairs cut over the N ranks by index range (strong scaling) ----
+    strong = None
+    if not args.no_strong and n == LANES_PER_GPU:
+        total = 1 << args.strong_log2
+        slo, shi = shard.shard_range(total, rank, world)
+        m = shi - slo
+        sk = dev.synth_values(dev.empty(m, 1), SEED_SCALARS, slo, m, 0)
+        sr = dev.synth_values(dev.empty(m, 1), SEED_POINTS, slo, m, 0)
+        sJ = dev.scalar_mult_base(dev.empty(m, 3), sr, m)
+        sxy = dev.to_affine(dev.empty(m, 2), sJ, m)
+        sP = dev.from_affine(sJ, sxy, m)                      # in place of the temporary
+        del sr, sxy
+        sout = dev.empty(m, 3)
+        torch.cuda.synchronize()
+        shard.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        dev.scalar_mult(sout, sk, sP, m)
+        s1.record()
+        torch.cuda.synchronize()
+        st_ms = shard.max_over_ranks(s0.elapsed_time(s1))
+        try:
+            s_ok, s_checked = spot_check(orc, sk, sP, sout, slo, m, SEED_SCALARS)
+        except Exception as ex:  # pragma: no cover
+            s_ok, s_checked = False, 0
+        s_all = shard.min_over_ranks(1.0 if s_ok else 0.0) == 1.0
+        peak_all = shard.sum_over_ranks(peak_wide)
+        strong = {"lanes_total": total, "lanes_this_rank": m, "ms": st_ms, "scalar_mults_per_s": total / st_ms * 1e3,
+                  "frac_of_imad_peak": total * MAC32_PER_SCALAR_MULT / (st_ms * 1e-3) / peak_all,
+                  "parity_vs_oracle": ("ok (%d ranks x %d lanes)" % (world, s_checked)) if s_all else "MISMATCH",
+                  "note": "BASELINE configs[4]: one pass over 2^%d pairs, inputs generated on the device from the seeds, "
+                          "index-range shards (ecsimd_b200.shard.shard_range), time = max over ranks" % args.strong_log2}
+        parity_all = parity_all and s_all
+        del sk, sP, sout, sJ
+        torch.cuda.empty_cache()
 
     # ---- secondary kernels of the path (config 1): streaming mulmod and register-resident mulmod ---------
     aux = {}
+    if strong is not None:
+        aux["strong_2^%d" % args.strong_log2] = strong
     if rank == 0 and world == 1:
         # what the reference's own bench times (benchs/curve_group.cpp:28-46): scalar_mult(...).to_affine(), host
         # buffers in the reference's pack layout -- fused entry point against the two separate calls
@@ -422,7 +522,7 @@ def main():
         del a, b, o1, flush
 
     if rank != 0:
-        return 0
+        return 0 if parity_all else 1
 
     cpu = None
     p256_ref = None
@@ -431,19 +531,22 @@ def main():
         cpu, _ = cpu_reference_rate(12.0, cores)
         p256_ref = openssl_rate(cores)
 
+    sm_mhz = float(clocks.get("sm_max_mhz") or 1965.0)
+    paper_peak = sms * 4 * 32 / 4.0 * sm_mhz * 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "scalar_mult_p256 variable-base, 2^%d (k,P) pairs per GPU per step (BASELINE configs[2])" % (n.bit_length() - 1),
-                   "lanes_per_gpu": n, "layout": "SOA planes in HBM", "parallelism": "index-range shards, no collective",
-                   "l2": "inputs+outputs per step = %d MiB > 126 MB L2" % (n * 224 >> 20), "quirk_exact": True},
+        "config": _config(n), "collective": "none (gloo carries the barrier and three host scalars)",
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_wide / 1e12, "unit": "TMAC32/s", "frac": achieved / peak_wide,
                      "traffic": _ladder_traffic(), "kernel": "k_scalar_mult_sync", "kernel_ms": kernel_ms,
                      "peak_source": "IMAD.WIDE.U32 rate measured live by ecb200_microbench on this GPU (not in MEASURED_PEAKS.json)",
+                     "peak_paper": paper_peak / 1e12, "frac_paper": achieved / paper_peak,
+                     "peak_paper_source": "%d SMs x 4 sub-partitions x 32 lanes / 4 clk x %.0f MHz (one IMAD.WIDE per sub-partition every 4 clocks)" % (sms, sm_mhz),
                      "algorithmic_mac32_per_lane": MAC32_PER_SCALAR_MULT},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128 * world, "d2h_bytes_per_step": n * 96 * world,
                 "steps": e2e_steps, "layout": "reference pack4, pinned host buffers", "matches_device_path": e2e_ok},
+        "e2e_pageable": e2e_pageable,
         "gpu_launches": launches, "clocks": clocks, "parity_vs_oracle": parity, "aux": aux,
     }
     if cpu:
@@ -451,7 +554,7 @@ def main():
     if p256_ref:
         line["p256_ref_openssl"] = p256_ref
     print(json.dumps(line), flush=True)
-    return 0
+    return 0 if parity_all else 1
 
 
 def _ladder_traffic():

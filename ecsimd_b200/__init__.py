@@ -13,4 +13,4 @@ operator interface over it:
                             used only to own device memory and streams).
 """
 from . import capi  # noqa: F401
-from .capi import Ecb200Error, init, launch_count, shutdown  # noqa: F401
+from .capi import Ecb200Error, device_count, init, init_devices, launch_count, shutdown  # noqa: F401

@@ -23,6 +23,8 @@ _vp, _sz, _u32, _i = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int
 SYMBOLS = {
     "ecb200_abi_version": (_i, []),
     "ecb200_init": (_i, [_i]),
+    "ecb200_init_devices": (_i, [C.POINTER(C.c_int), _i]),
+    "ecb200_device_count": (_i, []),
     "ecb200_shutdown": (_i, []),
     "ecb200_last_error": (C.c_char_p, []),
     "ecb200_launch_count": (C.c_uint64, []),
@@ -104,6 +106,18 @@ def check(rc):
 
 def init(device=0):
     check(load().ecb200_init(device))
+
+
+def init_devices(devices):
+    """single-process multi-GPU: host-memory batches of the scalar multiplication are cut over `devices`
+    (include/ecb200.h: ecb200_init_devices); an empty list or one device restores single-device dispatch"""
+    devices = list(devices)
+    arr = (C.c_int * max(1, len(devices)))(*devices)
+    check(load().ecb200_init_devices(arr, len(devices)))
+
+
+def device_count():
+    return int(load().ecb200_device_count())
 
 
 def shutdown():

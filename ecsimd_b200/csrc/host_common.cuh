@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/ecb200.h"
@@ -14,7 +15,28 @@
 namespace ecb200 {
 
 void set_error(const char* fmt, ...);
+const char* last_error();
 extern std::atomic<uint64_t> g_launches;
+
+// Per-device state owned by the library (kernels_field.cu): its own stream-ordered memory pool (the
+// process-wide default pool is left alone), the fixed-base tables, the three pipeline streams of the
+// host-memory batch path with their pinned bounce buffers.  Created by ecb200_init / ecb200_init_devices
+// (or lazily by the first call on a device), released by ecb200_shutdown.
+constexpr int kMaxDevices = 64;
+struct DeviceCtx {
+  std::mutex mu;                        // guards the lazily created members below
+  bool ready = false;
+  int device = -1;
+  cudaMemPool_t pool = nullptr;
+  uint4* base_tab[2] = {nullptr, nullptr};   // [quirk] 2^16 ladder states of G
+  std::mutex pipe_mu;                   // one host-memory batch at a time per device
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+  void* bounce_in[3] = {nullptr, nullptr, nullptr};   // pinned staging for pageable caller buffers
+  void* bounce_out[3] = {nullptr, nullptr, nullptr};
+  size_t bounce_in_bytes = 0, bounce_out_bytes = 0;
+};
+// context of the calling thread's current device, created on first use; nullptr + error set on failure
+DeviceCtx* current_ctx();
 
 #define ECB_CUDA(expr)                                                                   \
   do {                                                                                   \
@@ -55,6 +77,7 @@ inline int check_common(size_t n, uint32_t flags) {
 // One call's worth of device temporaries (stream-ordered; freed on the same stream).
 struct Scratch {
   cudaStream_t stream;
+  DeviceCtx* ctx = nullptr;
   std::vector<void*> ptrs;
   explicit Scratch(cudaStream_t s) : stream(s) {}
   ~Scratch() {
@@ -62,9 +85,10 @@ struct Scratch {
   }
   int alloc(void** out, size_t bytes) {
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(out, bytes, stream);
+    if (!ctx && !(ctx = current_ctx())) return ECB200_ERR_CUDA;
+    cudaError_t e = cudaMallocFromPoolAsync(out, bytes, ctx->pool, stream);
     if (e != cudaSuccess) {
-      set_error("cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      set_error("cudaMallocFromPoolAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
       return e == cudaErrorMemoryAllocation ? ECB200_ERR_NOMEM : ECB200_ERR_CUDA;
     }
     ptrs.push_back(*out);

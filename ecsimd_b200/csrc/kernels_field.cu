@@ -17,6 +17,62 @@ void set_error(const char* fmt, ...) {
   vsnprintf(t_err, sizeof t_err, fmt, ap);
   va_end(ap);
 }
+const char* last_error() { return t_err; }
+
+// ---- per-device contexts ---------------------------------------------------------------------------
+static DeviceCtx g_ctx[kMaxDevices];
+
+static int ensure_ctx(int device, DeviceCtx** out) {
+  if (device < 0 || device >= kMaxDevices) {
+    set_error("device %d is outside the %d contexts this library keeps", device, kMaxDevices);
+    return ECB200_ERR_ARG;
+  }
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!c.ready) {
+    int major = 0, minor = 0;
+    ECB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    ECB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10) {
+      set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, major, minor);
+      return ECB200_ERR_CUDA;
+    }
+    // the library's own pool for its stream-ordered temporaries, kept warm between calls; the process-wide
+    // default pool of the device is not touched
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    ECB_CUDA(cudaMemPoolCreate(&c.pool, &props));
+    unsigned long long thr = ~0ull;
+    ECB_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.device = device;
+    c.ready = true;
+  }
+  *out = &c;
+  return ECB200_OK;
+}
+
+DeviceCtx* current_ctx() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  DeviceCtx* c = nullptr;
+  return ensure_ctx(dev, &c) == ECB200_OK ? c : nullptr;
+}
+
+// devices a host-memory batch is cut over (ecb200_init_devices); empty = the calling thread's device only
+static std::mutex g_multi_mu;
+static std::vector<int> g_multi;
+std::vector<int> multi_devices() {
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  return g_multi;
+}
 
 enum FieldOp : int { OP_ADD, OP_SUB, OP_MUL, OP_SQR, OP_SHL, OP_NEG, OP_FROMC, OP_TOC, OP_INV, OP_MULCHAIN };
 
@@ -450,7 +506,10 @@ static int bytes_call(void* vals, void* bytes, int ncoord, size_t n, uint32_t fl
   }
   return ECB200_OK;
 }
-namespace ecb200 { int release_base_tables(); }
+namespace ecb200 {
+int release_device_resources(DeviceCtx* c);   // kernels_point.cu: fixed-base tables, pipeline streams, bounce buffers
+int prebuild_base_tables(DeviceCtx* c);
+}
 
 extern "C" {
 
@@ -466,29 +525,58 @@ int ecb200_init(int device) {
     return ECB200_ERR_ARG;
   }
   ECB_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  ECB_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
-    return ECB200_ERR_CUDA;
+  DeviceCtx* c = nullptr;
+  int rc = ensure_ctx(device, &c);
+  if (rc) return rc;
+  // the fixed-base tables are built here, so that no later ECB200_MEM_DEVICE call has to synchronise
+  return prebuild_base_tables(c);
+}
+
+int ecb200_init_devices(const int* devices, int count) {
+  if (count < 0 || (count > 0 && !devices)) {
+    set_error("bad device list");
+    return ECB200_ERR_ARG;
   }
-  // keep stream-ordered temporaries cached in the pool between calls
-  cudaMemPool_t pool;
-  ECB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  unsigned long long thr = ~0ull;
-  ECB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  for (int i = 0; i < count; i++)
+    for (int j = 0; j < i; j++)
+      if (devices[i] == devices[j]) {
+        set_error("device %d listed twice", devices[i]);
+        return ECB200_ERR_ARG;
+      }
+  for (int i = count - 1; i >= 0; i--) {   // ends on devices[0]: it becomes the calling thread's device
+    int rc = ecb200_init(devices[i]);
+    if (rc) return rc;
+  }
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  g_multi.assign(devices, devices + count);
+  if (count <= 1) g_multi.clear();
   return ECB200_OK;
+}
+
+int ecb200_device_count(void) {
+  std::lock_guard<std::mutex> lock(g_multi_mu);
+  return g_multi.empty() ? 1 : (int)g_multi.size();
 }
 
 int ecb200_shutdown(void) {
   int device = 0;
   ECB_CUDA(cudaGetDevice(&device));
   ECB_CUDA(cudaDeviceSynchronize());
-  int rc = ecb200::release_base_tables();
+  if (device < 0 || device >= kMaxDevices) return ECB200_OK;
+  {
+    std::lock_guard<std::mutex> lock(g_multi_mu);
+    for (size_t i = 0; i < g_multi.size(); i++)
+      if (g_multi[i] == device) { g_multi.clear(); break; }   // back to single-device dispatch
+  }
+  DeviceCtx& c = g_ctx[device];
+  int rc = release_device_resources(&c);
   if (rc) return rc;
-  cudaMemPool_t pool;
-  ECB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  ECB_CUDA(cudaMemPoolTrimTo(pool, 0));
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (c.ready) {
+    ECB_CUDA(cudaMemPoolDestroy(c.pool));
+    c.pool = nullptr;
+    c.ready = false;   // re-created by the next call on this device
+  }
   return ECB200_OK;
 }
 

@@ -8,6 +8,8 @@
 // noise there.
 #include <cstdlib>
 #include <mutex>
+#include <string>
+#include <thread>
 
 #include "host_common.cuh"
 #include "layout.cuh"
@@ -295,47 +297,66 @@ constexpr int kLadderThreads = 512;
 static bool ladder_has_layout(int L, bool q) { return L == L_SOA || q; }
 
 // Fixed-base table (BASELINE config 4): 2^kBaseTabW ladder states of G, 160 bytes each (10 MiB:
-// resident in the 126 MB L2 while a batch runs), built on first use per device and quirk mode.
+// resident in the 126 MB L2 while a batch runs), one per device and quirk mode, kept in the device's
+// context.  ecb200_init builds them (so that a later ECB200_MEM_DEVICE call never synchronises); a device
+// used without ecb200_init builds its table on the first fixed-base call, with one stream synchronisation.
 // ECB200_BASE_TABLE=0 in the environment selects the plain ladder with P = G.
 constexpr int kBaseTabW = 16;
-struct BaseTable {
-  uint4* tab[2] = {nullptr, nullptr};  // [quirk]
-  int device = -1;
-};
-static std::mutex g_base_mu;
-static BaseTable g_base[16];
-static int base_table(bool q, cudaStream_t s, const uint4** out) {
+static bool base_table_enabled() {
   static const bool enabled = [] { const char* e = getenv("ECB200_BASE_TABLE"); return !(e && e[0] == '0'); }();
-  *out = nullptr;
-  if (!enabled) return ECB200_OK;
-  int dev = 0;
-  ECB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return ECB200_OK;
-  std::lock_guard<std::mutex> lock(g_base_mu);
-  BaseTable& b = g_base[dev];
-  if (!b.tab[q]) {
-    uint4* t = nullptr;
-    ECB_CUDA(cudaMalloc(&t, ((size_t)1 << kBaseTabW) * 160));
-    const unsigned blocks = (1u << kBaseTabW) / 128;
-    if (q) k_build_base_table<true><<<blocks, 128, 0, s>>>(t, kBaseTabW);
-    else k_build_base_table<false><<<blocks, 128, 0, s>>>(t, kBaseTabW);
-    ECB_LAUNCH_CHECK();
-    ECB_CUDA(cudaStreamSynchronize(s));  // other streams may use the table from now on
-    b.tab[q] = t;
+  return enabled;
+}
+// caller holds c->mu
+static int build_base_table_locked(DeviceCtx* c, bool q, cudaStream_t s) {
+  if (c->base_tab[q]) return ECB200_OK;
+  uint4* t = nullptr;
+  ECB_CUDA(cudaMalloc(&t, ((size_t)1 << kBaseTabW) * 160));
+  const unsigned blocks = (1u << kBaseTabW) / 128;
+  if (q) k_build_base_table<true><<<blocks, 128, 0, s>>>(t, kBaseTabW);
+  else k_build_base_table<false><<<blocks, 128, 0, s>>>(t, kBaseTabW);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // other streams may use the table from now on
+  if (e != cudaSuccess) {
+    cudaFree(t);
+    set_error("building the fixed-base table failed: %s", cudaGetErrorString(e));
+    return ECB200_ERR_CUDA;
   }
-  *out = b.tab[q];
+  c->base_tab[q] = t;
   return ECB200_OK;
 }
-// ecb200_shutdown: give the current device's tables back (they are rebuilt on the next use)
-int release_base_tables() {
-  int dev = 0;
-  ECB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return ECB200_OK;
-  std::lock_guard<std::mutex> lock(g_base_mu);
-  for (auto& t : g_base[dev].tab) {
+static int base_table(bool q, cudaStream_t s, const uint4** out) {
+  *out = nullptr;
+  if (!base_table_enabled()) return ECB200_OK;
+  DeviceCtx* c = current_ctx();
+  if (!c) return ECB200_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(c->mu);   // per device: other devices' calls are not held up
+  int rc = build_base_table_locked(c, q, s);
+  if (rc) return rc;
+  *out = c->base_tab[q];
+  return ECB200_OK;
+}
+int prebuild_base_tables(DeviceCtx* c) {
+  if (!base_table_enabled()) return ECB200_OK;
+  std::lock_guard<std::mutex> lock(c->mu);
+  int rc = build_base_table_locked(c, true, nullptr);
+  return rc ? rc : build_base_table_locked(c, false, nullptr);
+}
+// ecb200_shutdown: give the device's tables, pipeline streams and bounce buffers back (re-created on demand)
+int release_device_resources(DeviceCtx* c) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  for (auto& t : c->base_tab) {
     if (t) ECB_CUDA(cudaFree(t));
     t = nullptr;
   }
+  for (int i = 0; i < 3; i++) {
+    if (c->pipe[i]) ECB_CUDA(cudaStreamDestroy(c->pipe[i]));
+    c->pipe[i] = nullptr;
+    if (c->bounce_in[i]) ECB_CUDA(cudaFreeHost(c->bounce_in[i]));
+    if (c->bounce_out[i]) ECB_CUDA(cudaFreeHost(c->bounce_out[i]));
+    c->bounce_in[i] = c->bounce_out[i] = nullptr;
+  }
+  c->bounce_in_bytes = c->bounce_out_bytes = 0;
   return ECB200_OK;
 }
 
@@ -368,47 +389,85 @@ static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int 
   return ECB200_ERR_ARG;
 }
 
-// Host-memory batches are cut into chunks of one full wave (148 SMs x 512 lanes) that rotate
-// over three internal streams: the PCIe copies and layout conversions of one chunk overlap the
-// ladder kernel of another, and the partial last wave of a chunk overlaps the next chunk's blocks.
+// Host-memory batches are cut into chunks of one full wave (148 SMs x 512 lanes) that rotate over the
+// device's three pipeline streams: the PCIe copies of one chunk overlap the ladder kernel of another, and
+// the partial last wave of a chunk overlaps the next chunk's blocks.
+//  * pinned (or registered) caller buffers are copied directly;
+//  * pageable caller buffers (std::vector, numpy: what the reference's callers hold) go through pinned
+//    bounce buffers owned by the library -- a cudaMemcpyAsync on pageable memory would block the host until
+//    the copy has happened, i.e. until the chunk's kernel has finished for the copy out, and serialise the
+//    pipeline.  The host copies of slot j happen while the other two slots run on the GPU.
+//  * affine = true appends to_affine to each chunk (ecb200_scalar_mult_p256_affine): the Jacobian result never
+//    crosses PCIe.
 constexpr size_t kChunkLanes = 148 * (size_t)kLadderThreads;
-struct PipeStreams {
-  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-  int device = -1;
-};
-static int pipe_streams(cudaStream_t** out) {
-  static thread_local PipeStreams ps;
-  int dev = 0;
-  ECB_CUDA(cudaGetDevice(&dev));
-  if (ps.device != dev) {
-    for (auto& st : ps.s) ECB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    ps.device = dev;
+static int pipe_resources(DeviceCtx* c, bool bounce) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  for (int i = 0; i < 3; i++)
+    if (!c->pipe[i]) ECB_CUDA(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+  if (bounce && !c->bounce_in[0]) {
+    c->bounce_in_bytes = kChunkLanes * 128;
+    c->bounce_out_bytes = kChunkLanes * 96;
+    for (int i = 0; i < 3; i++) {
+      ECB_CUDA(cudaHostAlloc(&c->bounce_in[i], c->bounce_in_bytes, cudaHostAllocDefault));
+      ECB_CUDA(cudaHostAlloc(&c->bounce_out[i], c->bounce_out_bytes, cudaHostAllocDefault));
+    }
   }
-  *out = ps.s;
   return ECB200_OK;
 }
+static bool is_pageable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
 
-static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, cudaStream_t user) {
+static int scalar_mult_call(void* out, const void* k, const void* P, int mode, int k_bcast, size_t n, uint32_t flags, void* stream);
+
+static int host_pipeline_body(DeviceCtx* c, void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, bool affine, bool bounce) {
   const int L = layout_of(flags);
   const bool q = quirk_on(flags);
   const bool native = ladder_has_layout(L, q);
   const bool use_table = (flags & ECB200_NO_BASE_TABLE) == 0;
-  cudaStream_t* ss = nullptr;
-  int rc = pipe_streams(&ss);
-  if (rc) return rc;
-  ECB_CUDA(cudaStreamSynchronize(user));  // host buffers are the caller's: order after its pending work
-  size_t c = 0;
-  for (size_t lo = 0; lo < n; lo += kChunkLanes, c++) {
+  const uint32_t dflags = (flags & ~ECB200_MEM_MASK) | ECB200_MEM_DEVICE;
+  const size_t out_lane = affine ? 64 : 96;
+  cudaStream_t* ss = c->pipe;
+  size_t done_lo[3] = {0, 0, 0}, done_m[3] = {0, 0, 0};   // chunk whose results wait in bounce_out[j]
+  int rc;
+  size_t ci = 0;
+  for (size_t lo = 0; lo < n; lo += kChunkLanes, ci++) {
     const size_t m = (n - lo < kChunkLanes) ? n - lo : kChunkLanes;
-    cudaStream_t s = ss[c % 3];
+    const int j = (int)(ci % 3);
+    cudaStream_t s = ss[j];
+    const char* src_k = (const char*)k + lo * 32;
+    const char* src_P = P ? (const char*)P + lo * 96 : nullptr;
+    char* dst = (char*)out + lo * out_lane;
+    if (bounce) {
+      if (ci >= 3) {   // slot j is free again once its previous chunk has left the GPU
+        ECB_CUDA(cudaStreamSynchronize(s));
+        memcpy((char*)out + done_lo[j] * out_lane, c->bounce_out[j], done_m[j] * out_lane);
+      }
+      memcpy(c->bounce_in[j], src_k, m * 32);
+      src_k = (const char*)c->bounce_in[j];
+      if (mode == 0) {
+        memcpy((char*)c->bounce_in[j] + kChunkLanes * 32, src_P, m * 96);
+        src_P = (const char*)c->bounce_in[j] + kChunkLanes * 32;
+      }
+      dst = (char*)c->bounce_out[j];
+      done_lo[j] = lo;
+      done_m[j] = m;
+    }
     Scratch sc(s);
-    void *rk, *rP = nullptr, *ro;
+    sc.ctx = c;
+    void *rk, *rP = nullptr, *ro, *rxy = nullptr;
     if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&ro, operand_bytes(m, 3)))) return rc;
     // LANE and PACK4 are both contiguous per group of 4 lanes: a chunk is a byte range
-    ECB_CUDA(cudaMemcpyAsync(rk, (const char*)k + lo * 32, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
+    ECB_CUDA(cudaMemcpyAsync(rk, src_k, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
     if (mode == 0) {
       if ((rc = sc.alloc(&rP, operand_bytes(m, 3)))) return rc;
-      ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
+      ECB_CUDA(cudaMemcpyAsync(rP, src_P, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
     }
     if (native) {
       if ((rc = launch_ladder(L, ro, rk, rP, mode, 0, m, q, s, use_table))) return rc;
@@ -423,10 +482,91 @@ static int scalar_mult_host_pipelined(void* out, const void* k, const void* P, i
       if ((rc = launch_ladder(L_SOA, so, sk, sP, mode, 0, m, q, s, use_table))) return rc;
       if ((rc = convert_from_soa(L, ro, so, m, 3, s))) return rc;
     }
-    ECB_CUDA(cudaMemcpyAsync((char*)out + lo * 96, ro, operand_bytes(m, 3), cudaMemcpyDeviceToHost, s));
+    const void* res = ro;
+    if (affine) {
+      if ((rc = sc.alloc(&rxy, operand_bytes(m, 2)))) return rc;
+      if ((rc = ecb200_to_affine(rxy, ro, m, dflags, s))) return rc;
+      res = rxy;
+    }
+    ECB_CUDA(cudaMemcpyAsync(dst, res, m * out_lane, cudaMemcpyDeviceToHost, s));
   }
-  for (int i = 0; i < 3; i++) ECB_CUDA(cudaStreamSynchronize(ss[i]));
+  for (int j = 0; j < 3; j++) {
+    ECB_CUDA(cudaStreamSynchronize(ss[j]));
+    if (bounce && done_m[j]) memcpy((char*)out + done_lo[j] * out_lane, c->bounce_out[j], done_m[j] * out_lane);
+  }
   return ECB200_OK;
+}
+
+// one device: the calling thread's current one
+static int host_pipeline(void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, bool affine) {
+  DeviceCtx* c = current_ctx();
+  if (!c) return ECB200_ERR_CUDA;
+  const bool bounce = is_pageable(k) || is_pageable(P) || is_pageable(out);
+  int rc = pipe_resources(c, bounce);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(c->pipe_mu);
+  rc = host_pipeline_body(c, out, k, P, mode, n, flags, affine, bounce);
+  if (rc) {
+    // a chunk failed: earlier chunks are still in flight and use the caller's buffers -- wait for them
+    // before handing the error back (the message of the first failure is kept)
+    char msg[512];
+    snprintf(msg, sizeof msg, "%s", last_error());
+    for (int j = 0; j < 3; j++) cudaStreamSynchronize(c->pipe[j]);
+    cudaGetLastError();
+    set_error("%s", msg);
+  }
+  return rc;
+}
+
+// ecb200_init_devices: the batch is cut into one contiguous index range per device (lanes are independent:
+// include/ecsimd/bignum.h:101-102), each range on its own host thread through that device's pipeline.
+std::vector<int> multi_devices();
+static int host_pipeline_multi(const std::vector<int>& devs, void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, bool affine) {
+  const size_t D = devs.size();
+  const size_t out_lane = affine ? 64 : 96;
+  // ranges in units of 512 lanes (whole thread blocks; also a multiple of the 4-lane packs)
+  const size_t units = (n + kLadderThreads - 1) / kLadderThreads;
+  std::vector<size_t> lo(D + 1);
+  for (size_t d = 0; d <= D; d++) {
+    const size_t u = units * d / D;
+    lo[d] = (u * kLadderThreads < n) ? u * kLadderThreads : n;
+  }
+  lo[D] = n;
+  std::vector<int> rcs(D, ECB200_OK);
+  std::vector<std::string> msgs(D);
+  int prev = 0;
+  ECB_CUDA(cudaGetDevice(&prev));
+  auto work = [&](size_t d) {
+    const size_t a = lo[d], m = lo[d + 1] - lo[d];
+    if (m == 0) return;
+    cudaError_t e = cudaSetDevice(devs[d]);
+    if (e != cudaSuccess) {
+      rcs[d] = ECB200_ERR_CUDA;
+      msgs[d] = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e);
+      return;
+    }
+    rcs[d] = host_pipeline((char*)out + a * out_lane, (const char*)k + a * 32, P ? (const char*)P + a * 96 : nullptr, mode, m, flags, affine);
+    if (rcs[d]) msgs[d] = last_error();
+  };
+  std::vector<std::thread> th;
+  for (size_t d = 1; d < D; d++) th.emplace_back(work, d);
+  work(0);
+  for (auto& t : th) t.join();
+  ECB_CUDA(cudaSetDevice(prev));
+  for (size_t d = 0; d < D; d++)
+    if (rcs[d]) {
+      set_error("device %d: %s", devs[d], msgs[d].c_str());
+      return rcs[d];
+    }
+  return ECB200_OK;
+}
+
+// host-memory batch of the scalar multiplication (optionally followed by to_affine)
+static int host_batch(void* out, const void* k, const void* P, int mode, size_t n, uint32_t flags, bool affine, cudaStream_t user) {
+  ECB_CUDA(cudaStreamSynchronize(user));  // host buffers are the caller's: order after its pending work
+  const std::vector<int> devs = multi_devices();
+  if (devs.size() > 1 && n >= 2 * kChunkLanes) return host_pipeline_multi(devs, out, k, P, mode, n, flags, affine);
+  return host_pipeline(out, k, P, mode, n, flags, affine);
 }
 
 static int scalar_mult_call(void* out, const void* k, const void* P, int mode, int k_bcast, size_t n, uint32_t flags, void* stream) {
@@ -438,7 +578,7 @@ static int scalar_mult_call(void* out, const void* k, const void* P, int mode, i
     return ECB200_ERR_ARG;
   }
   if (!on_device(flags) && layout_of(flags) != L_SOA && !k_bcast && n > kChunkLanes)
-    return scalar_mult_host_pipelined(out, k, P, mode, n, flags, (cudaStream_t)stream);
+    return host_batch(out, k, P, mode, n, flags, false, (cudaStream_t)stream);
   const int L = layout_of(flags);
   const bool q = quirk_on(flags);
   // native layout: the kernel reads/writes the caller's layout (only the memory space is staged)
@@ -561,30 +701,23 @@ static int scalar_mult_affine_call(void* out_xy, const void* k, const void* P, i
     if ((rc = scalar_mult_call(J, k, P, mode, 0, n, flags, stream))) return rc;
     return ecb200_to_affine(out_xy, J, n, flags, stream);
   }
+  // LANE and PACK4 are contiguous per group of 4 lanes (a chunk is a byte range): the chunked pipeline
+  if (layout_of(flags) != L_SOA) return host_batch(out_xy, k, P, mode, n, flags, true, user);
+  // planar host buffers: one pass through device temporaries
   const uint32_t dflags = (flags & ~ECB200_MEM_MASK) | ECB200_MEM_DEVICE;
-  const int L = layout_of(flags);
-  // LANE and PACK4 are contiguous per group of 4 lanes (a chunk is a byte range); SOA planes are not
-  const size_t chunk = (L == L_SOA) ? n : kChunkLanes;
-  cudaStream_t* ss = nullptr;
-  if ((rc = pipe_streams(&ss))) return rc;
-  ECB_CUDA(cudaStreamSynchronize(user));  // host buffers are the caller's: order after its pending work
-  size_t c = 0;
-  for (size_t lo = 0; lo < n; lo += chunk, c++) {
-    const size_t m = (n - lo < chunk) ? n - lo : chunk;
-    cudaStream_t s = ss[c % 3];
-    Scratch sc(s);
-    void *rk, *rP = nullptr, *rJ, *rxy;
-    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&rJ, operand_bytes(m, 3))) || (rc = sc.alloc(&rxy, operand_bytes(m, 2)))) return rc;
-    ECB_CUDA(cudaMemcpyAsync(rk, (const char*)k + lo * 32, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
-    if (mode == 0) {
-      if ((rc = sc.alloc(&rP, operand_bytes(m, 3)))) return rc;
-      ECB_CUDA(cudaMemcpyAsync(rP, (const char*)P + lo * 96, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
-    }
-    if ((rc = scalar_mult_call(rJ, rk, rP, mode, 0, m, dflags, s))) return rc;
-    if ((rc = ecb200_to_affine(rxy, rJ, m, dflags, s))) return rc;
-    ECB_CUDA(cudaMemcpyAsync((char*)out_xy + lo * 64, rxy, operand_bytes(m, 2), cudaMemcpyDeviceToHost, s));
+  ECB_CUDA(cudaStreamSynchronize(user));
+  Scratch sc(user);
+  void *rk, *rP = nullptr, *rJ, *rxy;
+  if ((rc = sc.alloc(&rk, operand_bytes(n, 1))) || (rc = sc.alloc(&rJ, operand_bytes(n, 3))) || (rc = sc.alloc(&rxy, operand_bytes(n, 2)))) return rc;
+  ECB_CUDA(cudaMemcpyAsync(rk, k, operand_bytes(n, 1), cudaMemcpyHostToDevice, user));
+  if (mode == 0) {
+    if ((rc = sc.alloc(&rP, operand_bytes(n, 3)))) return rc;
+    ECB_CUDA(cudaMemcpyAsync(rP, P, operand_bytes(n, 3), cudaMemcpyHostToDevice, user));
   }
-  for (int i = 0; i < 3; i++) ECB_CUDA(cudaStreamSynchronize(ss[i]));
+  if ((rc = scalar_mult_call(rJ, rk, rP, mode, 0, n, dflags, user))) return rc;
+  if ((rc = ecb200_to_affine(rxy, rJ, n, dflags, user))) return rc;
+  ECB_CUDA(cudaMemcpyAsync(out_xy, rxy, operand_bytes(n, 2), cudaMemcpyDeviceToHost, user));
+  ECB_CUDA(cudaStreamSynchronize(user));
   return ECB200_OK;
 }
 

@@ -143,8 +143,8 @@ def scalar_mult_affine(k, P=None, layout="lane", quirk=True, table=True):
     k = _in(k)
     n = lanes_of(k, layout, 1)
     out = np.zeros(_shape(layout, n, 2), np.uint32)
-    Pp = None if P is None else capi._p(_in(P))
-    capi.call("ecb200_scalar_mult_p256_affine", capi._p(out), capi._p(k), Pp, n, _flags(layout, quirk) | (0 if table else 0x200), None)
+    P = None if P is None else _in(P)   # keep the converted array alive for the duration of the call
+    capi.call("ecb200_scalar_mult_p256_affine", capi._p(out), capi._p(k), capi._p(P), n, _flags(layout, quirk) | (0 if table else 0x200), None)
     return out
 
 

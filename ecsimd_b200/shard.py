@@ -4,12 +4,14 @@ The path has no exchange step: lanes are independent (the reference's only
 "parallelism" is 4 independent SIMD lanes, include/ecsimd/bignum.h:101-102), so
 a batch of n lanes is cut into `world` contiguous ranges, each rank runs the
 same kernels on its own range, and nothing crosses NVLink.  torch.distributed
-is used for the rendezvous, the start barrier and the max-over-ranks reduction
-of the device time only.
+is used for the rendezvous, the start barrier and the reduction of a few host
+scalars (max of the device time, sum of lanes, min of the parity verdicts)
+only -- over the `gloo` backend on CPU tensors: no NCCL communicator is created
+and no collective kernel runs on any GPU.
 """
 import os
 
-ALIGN = 128  # lanes per thread block of the scalar-mult kernel
+ALIGN = 128  # shard boundaries fall on multiples of 128 lanes (whole 4-lane packs, whole warps)
 
 
 def shard_range(n, rank, world, align=ALIGN):
@@ -27,19 +29,12 @@ def env_rank_world():
 
 
 def init_distributed(backend=None):
-    """Rendezvous from the torchrun environment (MASTER_ADDR/MASTER_PORT/RANK/WORLD_SIZE)."""
-    import torch
+    """Rendezvous from the torchrun environment (MASTER_ADDR/MASTER_PORT/RANK/WORLD_SIZE); gloo unless told otherwise."""
     import torch.distributed as dist
     rank, world, local = env_rank_world()
     if world > 1 and not dist.is_initialized():
-        if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        kw = {}
-        if backend == "nccl":
-            torch.cuda.set_device(local)
-            kw["device_id"] = torch.device("cuda", local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+        dist.init_process_group(backend=backend or "gloo", rank=rank, world_size=world)
     return rank, world, local
 
 
@@ -57,6 +52,17 @@ def max_over_ranks(value, device=None):
         return float(value)
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def min_over_ranks(value, device=None):
+    """min of a python number over all ranks (a verdict that must hold on every rank)"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return float(t.item())
 
 

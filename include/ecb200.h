@@ -80,10 +80,23 @@ extern "C" {
 
 /* ---- library ------------------------------------------------------------- */
 int ecb200_abi_version(void);
-/* Select the CUDA device used by the calling thread for subsequent calls and
- * check that it is an sm_100 part. */
+/* Select the CUDA device used by the calling thread for subsequent calls, check that it is an
+ * sm_100 part, create the library's memory pool on it and build the fixed-base tables of
+ * ecb200_scalar_mult_p256_base (20 MiB, ~1 ms).  A device used without this call is set up by the first call
+ * that needs it (the first fixed-base call then synchronises its stream once). */
 int ecb200_init(int device);
-/* Release the staging buffers owned by the library on the current device. */
+/* Initialise several devices for single-process use -- the reference's caller is one process
+ * (benchs/curve_group.cpp:23-60).  Afterwards a HOST-memory batch (ECB200_LAYOUT_LANE or _PACK4) given to
+ * ecb200_scalar_mult_p256, ecb200_scalar_mult_p256_base or ecb200_scalar_mult_p256_affine is cut into one
+ * contiguous index range per device (lanes are independent: include/ecsimd/bignum.h:101-102), each range
+ * running on its own host thread through that device's three-stream pipeline; results are bit-identical to
+ * the single-device call.  ECB200_MEM_DEVICE calls keep using the calling thread's current device, which
+ * becomes devices[0].  count <= 1 restores single-device behaviour. */
+int ecb200_init_devices(const int* devices, int count);
+/* Number of devices host-memory batches are currently cut over (>= 1). */
+int ecb200_device_count(void);
+/* Release what the library owns on the current device: its memory pool, the fixed-base tables, the pipeline
+ * streams and pinned bounce buffers (all re-created by the next call that needs them). */
 int ecb200_shutdown(void);
 const char* ecb200_last_error(void);
 /* Number of kernels launched by this library in this process so far. */
