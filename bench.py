@@ -503,6 +503,21 @@ def main():
             "add_z2_1": _po(t_addz, 592, 288),
             "note": "algorithmic MAC32 / bytes per point: DBLU 1M+5S = 244 / 96+192; ZADDU 5M+2S = 392 / 192+192; TRPLU 6M+7S = 636 / 96+192; "
                     "ZDAU 9M+7S = 828 / 192+192; ADD_Z2_1 7M+4S = 592 / 192+96"}
+        # to_affine (1 inversion = 255 S + 128 M, then 1 S + 5 M), GFp::inverse, from_x (sqrt = 253 S + 34 M, ...)
+        xy2, inv2 = dev.empty(n2, 2), dev.empty(n2, 1)
+        ok2 = torch.empty(n2, dtype=torch.uint8, device=cuda)
+        t_aff = timed(lambda: dev.to_affine(xy2, J2, n2), 2)
+        t_inv = timed(lambda: dev.inverse(inv2, J2[4:6], n2), 2)
+        t_fx = timed(lambda: dev.from_x(inv2, ok2, xy2[0:2], n2), 2)
+
+        def _fo(t, mac, nbytes):
+            return {"ms": t, "lanes_per_s": n2 / t * 1e3, "algorithmic_mac32_per_lane": mac, "TMAC32_per_s": n2 * mac / t * 1e3 / 1e12,
+                    "frac_of_imad_peak": n2 * mac / t * 1e3 / peak_wide, "GBps": n2 * nbytes / t * 1e3 / 1e9}
+        aux["affine_ops_2^22"] = {"to_affine": _fo(t_aff, 255 * 36 + 128 * 64 + 36 + 5 * 64, 160), "gfp_inverse": _fo(t_inv, 255 * 36 + 128 * 64, 64),
+                                  "from_x": _fo(t_fx, 255 * 36 + 37 * 64, 65), "from_x_lanes_without_root": int(n2 - int(ok2.sum().item())),
+                                  "note": "integer-multiply bound (bound: imad); the pow chains follow the reference's LSB-first square-and-multiply (mgry_ops.h:44-86); "
+                                          "every x here is on the curve: the few lanes without a root are lanes where the reference's squaring defect breaks its own r^2 == y^2 check (gfp.h:46-54)"}
+        del xy2, inv2, ok2
         del r2, J2, P2, Q2, R2, O2
         # BASELINE configs[3]: generator, 2^24 scalars (same ladder with P = G: the only form that keeps the reference's (X:Y:Z))
         n4 = 1 << 24

@@ -518,16 +518,44 @@ __device__ __forceinline__ void fp_quirk_check(Lazy&, const QuirkAcc& q, const f
   }
 }
 
+// a^e through the reference's LSB-first square-and-multiply (mgry_ops.h:44-86): bit b of e multiplies the running
+// product by a^(2^b), and the base is squared nbits-1 times -- the same sequence of squarings (hence the same
+// squaring-defect lanes) as the reference.  e is a compile-time constant of the callers (p-2, (p+1)/4): the branch
+// on its bits is uniform.  MD = Lazy keeps the 2^-32 corner cases out of the loop (the caller re-runs a flagged
+// lane in Exact mode), which is what lets the loop body stay branch-free apart from the defect filter.
+template <bool QUIRK, class MD>
+__device__ __forceinline__ fe fp_pow_lsb(const fe& a, const uint32_t (&e)[8], int nbits, MD& md) {
+  fe res = fe_R(), base = a;
+#pragma unroll 1
+  for (int b = 0; b < nbits; b++) {
+    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base, md);
+    if (b < nbits - 1) base = fp_sqr<QUIRK>(base, md);
+  }
+  return res;
+}
+#define ECB200_PM2_WORDS {0xfffffffdu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 1u, 0xffffffffu}            /* p - 2 */
+#define ECB200_SQRT_EXP_WORDS {0u, 0u, 0x40000000u, 0u, 0u, 0x40000000u, 0xc0000000u, 0x3fffffffu}    /* (p+1)/4 = 2^254 - 2^222 + 2^190 + 2^94 */
+// GFp::inverse = a^(p-2)   gfp.h:42-44
+template <bool QUIRK, class MD>
+__device__ __forceinline__ fe fp_inv(const fe& a, MD& md) {
+  const uint32_t e[8] = ECB200_PM2_WORDS;
+  return fp_pow_lsb<QUIRK>(a, e, 256, md);
+}
+
 // gfp.h:60-64: opposite(a) = (p-1)R - (a - R)
 __device__ __forceinline__ fe fp_neg(const fe& a) { return fp_sub(fe_PM1R(), fp_sub(a, fe_R())); }
 
 // mgry.h:47-50 / :52-55
-__device__ __forceinline__ fe fp_from_classical(const fe& a) { return fp_mul(a, fe_RR()); }
-__device__ __forceinline__ fe fp_to_classical(const fe& a) {
+template <class MD>
+__device__ __forceinline__ fe fp_from_classical(const fe& a, MD& md) { return fp_mul(a, fe_RR(), md); }
+template <class MD>
+__device__ __forceinline__ fe fp_to_classical(const fe& a, MD& md) {
   fe one = fe_zero();
   one.v[0] = 1;
-  return fp_mul(a, one);  // (a * 1 + m p) / R == mgry_reduce(pad(a))
+  return fp_mul(a, one, md);  // (a * 1 + m p) / R == mgry_reduce(pad(a))
 }
+__device__ __forceinline__ fe fp_from_classical(const fe& a) { Exact e; return fp_from_classical(a, e); }
+__device__ __forceinline__ fe fp_to_classical(const fe& a) { Exact e; return fp_to_classical(a, e); }
 
 __device__ __forceinline__ void fe_cswap(uint32_t mask, fe& a, fe& b) {
 #pragma unroll

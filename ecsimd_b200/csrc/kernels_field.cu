@@ -76,19 +76,29 @@ std::vector<int> multi_devices() {
 
 enum FieldOp : int { OP_ADD, OP_SUB, OP_MUL, OP_SQR, OP_SHL, OP_NEG, OP_FROMC, OP_TOC, OP_INV, OP_MULCHAIN };
 
-// a^(p-2) with the reference's LSB-first square-and-multiply (mgry_ops.h:44-86): the
-// sequence of squarings (and so the squaring-defect lanes) is the same as in the reference.
+// The inversion runs in Lazy mode (fp_pow_lsb, fp256.cuh); a lane that met one of the 2^-32 corner cases is
+// recomputed from its input in Exact mode, out of line.
+template <bool QUIRK>
+__device__ __noinline__ void fp_inv_exact(uint32_t* r8, const uint32_t* a8) {
+  Exact md;
+  fe a;
+  for (int i = 0; i < 8; i++) a.v[i] = a8[i];
+  const fe r = fp_inv<QUIRK>(a, md);
+  for (int i = 0; i < 8; i++) r8[i] = r.v[i];
+}
 template <bool QUIRK>
 __device__ __forceinline__ fe fp_inv(const fe& a) {
-  // p - 2 = ffffffff 00000001 00000000 00000000 00000000 ffffffff ffffffff fffffffd
-  const uint32_t e[8] = {0xfffffffdu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 1u, 0xffffffffu};
-  fe res = fe_R(), base = a;
-#pragma unroll 1
-  for (int b = 0; b < 256; b++) {
-    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base);
-    if (b < 255) base = fp_sqr<QUIRK>(base);
+  Lazy md;
+  fe r = fp_inv<QUIRK>(a, md);
+  if (__builtin_expect(md.flagged(), 0)) {
+    uint32_t in[8], out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) in[i] = a.v[i];
+    fp_inv_exact<QUIRK>(out, in);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = out[i];
   }
-  return res;
+  return r;
 }
 
 template <int L, int OP, bool QUIRK>

@@ -62,13 +62,19 @@ __device__ __noinline__ void point_op_exact(void* out1, void* out2, const void* 
   point_store<OP>(out1, out2, n, i, r, w);
 }
 
-// Block size per op: the multiply-bound ZDAU (50 KB of straight-line code) runs best as one
-// 512-thread block per SM, whose warps stay close together and share instruction-cache lines
-// (0.82 vs 0.87 ms at 2^22 points); the shorter ops, which lean on HBM, prefer many small blocks.
+// Block size per op: the multiply-bound ZDAU (50 KB of straight-line code) runs as two 256-thread blocks
+// per SM: warps of a block stay close together and share instruction-cache lines, and while one block
+// loads its 384 bytes per point or stores its results the other one multiplies (one 512-thread block per SM
+// serialised load -> compute -> store: 0.47 of the IMAD peak against the ladder's 0.57 for the same formula).
+// The shorter ops, which lean on HBM, prefer many small blocks.
+#ifndef ECB200_ZDAU_THREADS
+#define ECB200_ZDAU_THREADS 256
+#define ECB200_ZDAU_BLOCKS 2
+#endif
 template <int OP>
-struct PointThreads { static constexpr int value = (OP == PO_ZDAU) ? 512 : 128; };
+struct PointThreads { static constexpr int value = (OP == PO_ZDAU) ? ECB200_ZDAU_THREADS : 128; static constexpr int blocks = (OP == PO_ZDAU) ? ECB200_ZDAU_BLOCKS : 1; };
 template <int OP, bool QUIRK>
-__global__ void __launch_bounds__(PointThreads<OP>::value) k_point(void* out1, void* out2, const void* A, const void* B, size_t n) {
+__global__ void __launch_bounds__(PointThreads<OP>::value, PointThreads<OP>::blocks) k_point(void* out1, void* out2, const void* A, const void* B, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Lazy md;
@@ -150,47 +156,73 @@ __global__ void __launch_bounds__(128) k_build_base_table(uint4* __restrict__ ta
   for (int c = 0; c < 10; c++) e[c] = make_uint4(st[4 * c], st[4 * c + 1], st[4 * c + 2], st[4 * c + 3]);
 }
 
+// to_affine (jacobian_curve_point.h:33-42): invZ = z^(p-2); x = X*invZ^2; y = Y*invZ^3; to_classical.  255 squarings +
+// 128 + 6 multiplications per lane = 17 792 algorithmic MAC32 against 160 bytes: integer-multiply bound.  Lazy mode
+// with an out-of-line exact re-run of flagged lanes, like the point kernels.
+template <bool QUIRK, class MD>
+__device__ __forceinline__ void to_affine_compute(const jac& a, fe& x, fe& y, MD& md) {
+  const fe iz = fp_inv<QUIRK>(a.z, md);
+  const fe iz2 = fp_sqr<QUIRK>(iz, md);
+  const fe iz3 = fp_mul(iz2, iz, md);
+  x = fp_to_classical(fp_mul(a.x, iz2, md), md);
+  y = fp_to_classical(fp_mul(a.y, iz3, md), md);
+}
 template <bool QUIRK>
-__global__ void __launch_bounds__(128) k_to_affine(void* __restrict__ xy, const void* __restrict__ J, size_t n) {
+__device__ __noinline__ void to_affine_exact(void* xy, const void* J, size_t n, size_t i) {
+  Exact md;
+  fe x, y;
+  to_affine_compute<QUIRK>(load_jac(J, n, i), x, y, md);
+  S::store(xy, n, i, 2, 0, x);
+  S::store(xy, n, i, 2, 1, y);
+}
+template <bool QUIRK>
+__global__ void __launch_bounds__(256, 2) k_to_affine(void* __restrict__ xy, const void* __restrict__ J, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const jac a = load_jac(J, n, i);
-  // jacobian_curve_point.h:33-42: invZ = z^(p-2); x = X*invZ^2; y = Y*invZ^3; to_classical
-  const uint32_t e[8] = {0xfffffffdu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 1u, 0xffffffffu};
-  fe res = fe_R(), base = a.z;
-#pragma unroll 1
-  for (int b = 0; b < 256; b++) {
-    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base);
-    if (b < 255) base = fp_sqr<QUIRK>(base);
-  }
-  const fe iz2 = fp_sqr<QUIRK>(res);
-  const fe iz3 = fp_mul(iz2, res);
-  S::store(xy, n, i, 2, 0, fp_to_classical(fp_mul(a.x, iz2)));
-  S::store(xy, n, i, 2, 1, fp_to_classical(fp_mul(a.y, iz3)));
+  Lazy md;
+  fe x, y;
+  to_affine_compute<QUIRK>(load_jac(J, n, i), x, y, md);
+  if (__builtin_expect(md.flagged(), 0)) { to_affine_exact<QUIRK>(xy, J, n, i); return; }
+  S::store(xy, n, i, 2, 0, x);
+  S::store(xy, n, i, 2, 1, y);
 }
 
 // wide_curve_point::from_x / curve_group::compute_y (curve_point_ops.h:12-22, curve_group.h:43-58):
 // y = sqrt(x^3 - 3x + b) with sqrt = pow((p+1)/4) (gfp.h:46-54) through the reference's LSB-first
 // square-and-multiply (mgry_ops.h:44-86, same sequence of squarings), then the check r^2 == y^2.
 // ok[i] = 1 iff lane i has a square root (the reference answers per 4-lane pack: all four or none).
+// 255 squarings + 6 multiplications = 9 564 algorithmic MAC32 per lane.
+template <bool QUIRK, class MD>
+__device__ __forceinline__ void from_x_compute(const fe& xc, fe& y, uint8_t& ok, MD& md) {
+  const fe xm = fp_from_classical(xc, md);
+  const fe xpow3 = fp_mul(fp_sqr<QUIRK>(xm, md), xm, md);
+  const fe x3 = fp_add(fp_shl1(xm, md), xm, md);
+  const fe ypow2 = fp_sub(fp_add(xpow3, fe_BM(), md), x3);
+  const uint32_t e[8] = ECB200_SQRT_EXP_WORDS;
+  const fe res = fp_pow_lsb<QUIRK>(ypow2, e, 254, md);
+  ok = fe_eq(fp_sqr<QUIRK>(res, md), ypow2) ? 1 : 0;
+  y = fp_to_classical(res, md);
+}
 template <bool QUIRK>
-__global__ void __launch_bounds__(128) k_from_x(void* __restrict__ y, uint8_t* __restrict__ ok, const void* __restrict__ x, size_t n) {
+__device__ __noinline__ void from_x_exact(void* y, uint8_t* ok, const void* x, size_t n, size_t i) {
+  Exact md;
+  fe r;
+  uint8_t o;
+  from_x_compute<QUIRK>(S::load(x, n, i, 1, 0), r, o, md);
+  ok[i] = o;
+  S::store(y, n, i, 1, 0, r);
+}
+template <bool QUIRK>
+__global__ void __launch_bounds__(256, 2) k_from_x(void* __restrict__ y, uint8_t* __restrict__ ok, const void* __restrict__ x, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const fe xm = fp_from_classical(S::load(x, n, i, 1, 0));
-  const fe xpow3 = fp_mul(fp_sqr<QUIRK>(xm), xm);
-  const fe x3 = fp_add(fp_shl1(xm), xm);
-  const fe ypow2 = fp_sub(fp_add(xpow3, fe_BM()), x3);
-  // (p+1)/4 = 2^254 - 2^222 + 2^190 + 2^94
-  const uint32_t e[8] = {0u, 0u, 0x40000000u, 0u, 0u, 0x40000000u, 0xc0000000u, 0x3fffffffu};
-  fe res = fe_R(), base = ypow2;
-#pragma unroll 1
-  for (int b = 0; b < 254; b++) {
-    if ((e[b >> 5] >> (b & 31)) & 1u) res = fp_mul(res, base);
-    if (b < 253) base = fp_sqr<QUIRK>(base);
-  }
-  ok[i] = fe_eq(fp_sqr<QUIRK>(res), ypow2) ? 1 : 0;
-  S::store(y, n, i, 1, 0, fp_to_classical(res));
+  Lazy md;
+  fe r;
+  uint8_t o;
+  from_x_compute<QUIRK>(S::load(x, n, i, 1, 0), r, o, md);
+  if (__builtin_expect(md.flagged(), 0)) { from_x_exact<QUIRK>(y, ok, x, n, i); return; }
+  ok[i] = o;
+  S::store(y, n, i, 1, 0, r);
 }
 
 __global__ void __launch_bounds__(256) k_from_affine(void* __restrict__ J, const void* __restrict__ xy, size_t n) {
@@ -656,9 +688,9 @@ int ecb200_from_x(void* y, uint8_t* ok, const void* x, size_t n, uint32_t flags,
   if ((rc = st.in(x, 1, &din))) return rc;
   if ((rc = st.out(y, 1, &dout))) return rc;
   if (!on_device(flags) && (rc = st.sc.alloc(&dok, n))) return rc;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
-  if (quirk_on(flags)) k_from_x<true><<<blocks, 128, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
-  else k_from_x<false><<<blocks, 128, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (quirk_on(flags)) k_from_x<true><<<blocks, 256, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
+  else k_from_x<false><<<blocks, 256, 0, st.s>>>(dout, (uint8_t*)dok, din, n);
   ECB_LAUNCH_CHECK();
   if (!on_device(flags)) ECB_CUDA(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st.s));
   return st.finish();
@@ -674,9 +706,9 @@ int ecb200_to_affine(void* xy, const void* J, size_t n, uint32_t flags, void* st
   void* dout = nullptr;
   if ((rc = st.in(J, 3, &din))) return rc;
   if ((rc = st.out(xy, 2, &dout))) return rc;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
-  if (quirk_on(flags)) k_to_affine<true><<<blocks, 128, 0, st.s>>>(dout, din, n);
-  else k_to_affine<false><<<blocks, 128, 0, st.s>>>(dout, din, n);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (quirk_on(flags)) k_to_affine<true><<<blocks, 256, 0, st.s>>>(dout, din, n);
+  else k_to_affine<false><<<blocks, 256, 0, st.s>>>(dout, din, n);
   ECB_LAUNCH_CHECK();
   return st.finish();
 }

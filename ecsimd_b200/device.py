@@ -94,6 +94,17 @@ def scalar_mult_affine(xy, k, P, n, layout="soa", quirk=True):
     return xy
 
 
+def inverse(out, a, n, layout="soa", quirk=True):
+    capi.call("ecb200_gfp_inverse", out.data_ptr(), a.data_ptr(), n, _flags(layout, quirk), _stream())
+    return out
+
+
+def from_x(y, ok, x, n, layout="soa", quirk=True):
+    """y: (2, n, 4) classical y; ok: (n,) uint8 device tensor; x: classical x"""
+    capi.call("ecb200_from_x", y.data_ptr(), ok.data_ptr(), x.data_ptr(), n, _flags(layout, quirk), _stream())
+    return y, ok
+
+
 def from_affine(J, xy, n, layout="soa"):
     capi.call("ecb200_from_affine", J.data_ptr(), xy.data_ptr(), n, _flags(layout), _stream())
     return J

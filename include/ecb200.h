@@ -42,6 +42,11 @@
  *                        kernels are enqueued on `stream` (a cudaStream_t, may
  *                        be NULL for the default stream) and the call returns
  *                        without synchronising.
+ * SIDE CHANNELS: this library reproduces the reference's VALUES, not its constant-time property.  The
+ * variable-base ladder runs the same field operations for every scalar and addresses memory independently
+ * of it, but the squaring-defect filter and the 2^-32 corner cases of the conditional subtractions are
+ * data-dependent branches, and the fixed-base entry point indexes a table with scalar bits 1..16 unless
+ * ECB200_NO_BASE_TABLE is given.
  * ECB200_NO_QUIRK        compute mathematically exact squares instead of
  *                        reproducing the reference's lost-carry squaring defect
  *                        (include/ecsimd/mul.h:192-206).  Default (flag clear)

@@ -1,0 +1,3 @@
+// Source-compatibility shim: <ecsimd/curve_point_ops.h> of aguinet/ecsimd, served by the B200 engine's mirror header.
+#pragma once
+#include "../../ecsimd.hpp"

@@ -1,0 +1,3 @@
+// Source-compatibility shim: <ecsimd/mgry.h> of aguinet/ecsimd, served by the B200 engine's mirror header.
+#pragma once
+#include "../../ecsimd.hpp"

@@ -15,7 +15,8 @@ using WBN = WBN256;
 using WJCP = CurveGroup::WJCP;
 
 static int checks = 0;
-#define EXPECT_TRUE(c) do { ++checks; if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+// comparisons are per-lane masks as in the reference: a check holds when ALL four lanes agree
+#define EXPECT_TRUE(c) do { ++checks; if (!all(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 static WBN set1(const char* hex) { return WBN{bn_from_hex(hex)}; }
 
 int main() {
@@ -85,6 +86,49 @@ int main() {
     CurveGroup::scalar_mult_affine(aff.data(), ks.data(), P.data(), 64);
     CurveGroup::scalar_mult_affine(affg.data(), ks.data(), nullptr, 64);
     for (int i = 0; i < 64; i += 13) { EXPECT_TRUE(aff[i] == out[i].to_affine()); EXPECT_TRUE(affg[i] == aff[i]); }
+  }
+  {  // the rest of the mgry/ops + gfp + curve_point surface (mgry_ops.h:44-86, gfp.h:46-54, curve_point_ops.h:12-22,
+     // curve_group.h:31-58, ifelse.h, swap.h, literals.h)
+    using namespace ecsimd::literals;
+    const auto x = WBN{bn_from_bytes_BE<bignum_256>("ce11d601ec0e947529e66021a0cd3d57518d58d0d5f2eb7ed75805d78c986e60"_hex)};
+    const auto pt = wide_curve_point<Curve>::from_x(x);           // tests/curve_point.cpp:17-26
+    EXPECT_TRUE(pt.has_value());
+    EXPECT_TRUE(pt->y() == set1("f2a40cfbb248ae2c7749c76641b51b7137ccad8916931adf83b857e418fad591"));
+    const auto yy = CurveGroup::compute_y(x);
+    EXPECT_TRUE(yy.has_value() && all(*yy == pt->y()));
+    // one lane without a root empties the optional (all four lanes or nothing)
+    WBN xbad = x;
+    xbad.set(2, bignum_256::from(7));   // x = 7: x^3 - 3x + b is not a square mod p
+    EXPECT_TRUE(!wide_curve_point<Curve>::from_x(xbad).has_value());
+    // mgry_pow: a^(p-2) is the inverse, a^((p+1)/4) squared gives a back for a square
+    const auto a = gfp_p256::from_classical(x);
+    const auto pm2 = bn_from_hex("ffffffff00000001000000000000000000000000fffffffffffffffffffffffd");
+    EXPECT_TRUE(mgry_pow(a.wmbn(), pm2) == a.inverse().wmbn());
+    const auto sq = a.sqr();
+    const auto rt = sq.sqrt();
+    EXPECT_TRUE(rt.has_value() && all(rt->sqr() == sq));
+    // masks: if_else / swap_if / swap_if_same_z per lane
+    wide_mask m = wide_mask::splat(false);
+    m.set(1, true); m.set(3, true);
+    auto A = CurveGroup::WJG();
+    auto B2 = CurveGroup::DBLU(A);                                // A and B2 share Z
+    const auto A0 = A, B0 = B2;
+    const auto sel = if_else(m, A, B2);
+    for (int k = 0; k < 4; k++) EXPECT_TRUE(sel.x().wbn().get(k) == (m.get(k) ? A0 : B0).x().wbn().get(k));
+    swap_if_same_z(m, A, B2);
+    for (int k = 0; k < 4; k++) {
+      EXPECT_TRUE(A.y().wbn().get(k) == (m.get(k) ? B0 : A0).y().wbn().get(k));
+      EXPECT_TRUE(B2.x().wbn().get(k) == (m.get(k) ? A0 : B0).x().wbn().get(k));
+    }
+    swap_if(!m, A, B2);
+    swap_if(wide_mask::splat(true), A, B2);
+    swap_if_same_z(m, A, B2);
+    swap_if(!m, A, B2);                                            // back to (A0, B0) lane by lane
+    EXPECT_TRUE(B2 == A0);
+    EXPECT_TRUE(A == B0);
+    // Am, Bm: the curve constants in Montgomery form
+    EXPECT_TRUE(gfp_p256::from_classical(WBN{Curve::B()}).wbn() == WBN{CurveGroup::Bm()});
+    EXPECT_TRUE(gfp_p256::from_classical(WBN{Curve::A()}).wbn() == WBN{CurveGroup::Am()});
   }
   std::printf("ok %d\n", checks);
   return 0;
