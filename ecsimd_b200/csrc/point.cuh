@@ -249,7 +249,10 @@ __device__ __forceinline__ jac pt_scalar_mult_mode(const Src& src, MD& md) {
     fe_cswap(sw, qy, by);
     pt_zdau_xy<QUIRK>(bx, by, qx, qy, Z, md);
     prev = bit;
-    if (SYNC) __syncthreads();
+#ifndef ECB200_SYNC_EVERY
+#define ECB200_SYNC_EVERY 1
+#endif
+    if (SYNC && (ECB200_SYNC_EVERY == 1 || (b % ECB200_SYNC_EVERY) == 0)) __syncthreads();
   }
   fe_cswap(prev, qx, bx);
   fe_cswap(prev, qy, by);
