@@ -44,6 +44,63 @@ def regenerate():
         subprocess.run([sys.executable, gen], check=True, cwd=CSRC)
 
 
+# Kernels whose registers are re-coloured after ptxas (csrc/sass_recolor.py: IMAD.WIDE multiplicands and ALU sources
+# moved to different register banks; no instruction is added, removed or moved).  ECB200_RECOLOR=0 builds without the
+# pass, ECB200_RECOLOR=strict makes a failure of the pass fatal (default: ship the kernels as ptxas wrote them and
+# say so in recolor_report.json).
+RECOLOR = {"kernels_point.cu": "k_scalar_mult_sync"}
+RECOLOR_PLAN = os.path.join(CSRC, "recolor_plans.json")
+RECOLOR_REPORT = os.path.join(HERE, "recolor_report.json")
+
+
+def _compile_recolored(nvcc, src, obj, substr, verbose):
+    """nvcc -c with one extra step between ptxas and fatbinary: replay nvcc's own sub-commands (nvcc -dryrun) and
+    patch the .cubin in place."""
+    import json
+    import re
+    keep = os.path.join(OBJDIR, os.path.basename(src) + ".keep")
+    shutil.rmtree(keep, ignore_errors=True)
+    os.makedirs(keep)
+    dry = subprocess.run([nvcc] + NVCC_FLAGS + ["-dryrun", "--keep", "--keep-dir", keep, "-c", src, "-o", obj],
+                         capture_output=True, text=True, check=True).stderr
+    env = dict(os.environ)
+    cmds = []
+    for line in dry.splitlines():
+        if not line.startswith("#$ "):
+            continue
+        line = line[3:]
+        m = re.match(r"^([A-Za-z_][A-Za-z0-9_]*)=(.*)$", line)
+        if m and not cmds:
+            v = m.group(2).strip()
+            env[m.group(1)] = os.path.expandvars(v.replace('"', "")) if m.group(1) != "PATH" else v
+            continue
+        cmds.append(line)
+    env["PATH"] = env.get("PATH", os.environ["PATH"])
+    report = None
+    for c in cmds:
+        if verbose:
+            print(c[:160], flush=True)
+        subprocess.run(["bash", "-c", c], check=True, env=env, cwd=ROOT)
+        m = re.match(r'^ptxas .* -o "([^"]+\.cubin)"', c)
+        if m and os.environ.get("ECB200_RECOLOR", "1") != "0":
+            cubin = m.group(1)
+            sys.path.insert(0, CSRC)
+            try:
+                import sass_recolor
+                tmp = cubin + ".recolored"
+                report = sass_recolor.recolour_cubin(cubin, tmp, substr, plan_path=RECOLOR_PLAN, verbose=verbose)
+                os.replace(tmp, cubin)
+            except Exception as e:
+                if os.environ.get("ECB200_RECOLOR") == "strict":
+                    raise
+                print("WARNING: sass_recolor failed, shipping %s as ptxas wrote it: %s" % (substr, str(e)[:2000]), file=sys.stderr, flush=True)
+                report = {"error": str(e)[:2000]}
+            finally:
+                sys.path.remove(CSRC)
+    with open(RECOLOR_REPORT, "w") as f:
+        json.dump({"source": os.path.basename(src), "kernels": report}, f, indent=1)
+
+
 def build(force=False, verbose=False):
     regenerate()
     nvcc = _nvcc()
@@ -53,9 +110,14 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        if force or _newer(o, [s] + deps):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
+        if force or _newer(o, [s] + deps + ([os.path.join(CSRC, "sass_recolor.py")] if src in RECOLOR else [])):
+            if src in RECOLOR and os.environ.get("ECB200_RECOLOR", "1") != "0":
+                jobs.append(("recolor", s, o, RECOLOR[src]))
+            else:
+                jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
     def run(cmd):
+        if isinstance(cmd, tuple):
+            return _compile_recolored(nvcc, cmd[1], cmd[2], cmd[3], verbose)
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -348,9 +348,9 @@ static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t
   return (uint32_t)m == 0x7fffffffu;
 }
 
-// First-level filter.  Eight of the 28 cross products (ECB200_SQR_EXACT_PAIRS: every a_0*a_j and
-// a_1*a_7) are the first to land on their accumulator pair in fp_sqr_t9, so their exact high words
-// are there for free: fp_sqr_t9 folds them into qx (signed max, INT_MAX <=> hit).  The other 20 get
+// First-level filter.  Eight of the 28 cross products (ECB200_SQR_EXACT_PAIRS, written by gen_fp256.py: the two
+// chains of fp_sqr_t9 whose products all land on untouched accumulator pairs) leave their exact high words
+// in registers for free: fp_sqr_t9 folds them into qx (signed max, INT_MAX <=> hit).  The other 20 get
 // a necessary condition in fp32, one FFMA each: a hit needs a_i, a_j >= 2^31 and
 // a_i*a_j in [2^63 - 2^32, 2^63).  f(a) = as_float(0x3f000000 + (a >> 8)) is one LEA.HI; for a >= 2^31
 // it equals floor(a / 256) * 2^-23, i.e. a / 2^31 truncated to 24 bits, in [1, 2).  Then
@@ -361,18 +361,24 @@ static __device__ __noinline__ uint32_t fp_sqr_quirk_filter_exact(const uint32_t
 // 3-input min keeps it to one FFMA + half a VIMNMX3 per pair; `m` chains through a group of squarings.
 // False positives: ~2e-6 per square (the 16-bit integer form this replaces: 8.5e-4, i.e. a cold-path
 // excursion in one ladder step out of six per warp).
+__host__ __device__ constexpr bool fp_sqr_pair_is_exact(int i, int j) {
+  constexpr int ex[8][2] = ECB200_SQR_EXACT_PAIRS;
+  for (int k = 0; k < 8; k++)
+    if (ex[k][0] == i && ex[k][1] == j) return true;
+  return false;
+}
 #define ECB200_QF_THRESHOLD 0x35000000u
 __device__ __forceinline__ uint32_t fp_sqr_quirk_filter(const fe& a, uint32_t m = 0xffffffffu) {
   float f[8];
 #pragma unroll
-  for (int i = 1; i < 8; i++) f[i] = __uint_as_float((a.v[i] >> 8) + 0x3f000000u);
+  for (int i = 0; i < 8; i++) f[i] = __uint_as_float((a.v[i] >> 8) + 0x3f000000u);
   uint32_t pend = 0xffffffffu;
   bool have = false;
 #pragma unroll
-  for (int i = 1; i < 7; i++) {
+  for (int i = 0; i < 7; i++) {
 #pragma unroll
     for (int j = i + 1; j < 8; j++) {
-      if (i == 1 && j == 7) continue;  // in qx
+      if (fp_sqr_pair_is_exact(i, j)) continue;  // in qx
       const uint32_t y = __float_as_uint(__fmaf_rn(-f[i], f[j], 2.0f));
       if (have) { m = __vimin3_u32(m, pend, y); have = false; }
       else { pend = y; have = true; }
@@ -401,7 +407,7 @@ __device__ __forceinline__ uint32_t fp_sqr_quirk_filter_all(const fe& a) {
   }
   return m;
 }
-static_assert(sizeof((const int[][2])ECB200_SQR_EXACT_PAIRS) == 8 * 2 * sizeof(int), "fp_sqr_quirk_filter assumes the 8 exact pairs (0,j), (1,7)");
+static_assert(sizeof((const int[][2])ECB200_SQR_EXACT_PAIRS) == 8 * 2 * sizeof(int), "fp_sqr_pair_is_exact reads exactly 8 exact pairs");
 
 template <bool QUIRK, class M>
 __device__ __forceinline__ fe fp_sqr_core(const fe& a, M& mode, uint32_t& qx) {
@@ -490,10 +496,12 @@ template <bool QUIRK>
 __device__ __forceinline__ void fp_quirk_check(Lazy&, const QuirkAcc& q, const fe& a, fe& ra, const fe& b, fe& rb) {
   if (QUIRK) {
     if (__builtin_expect(fp_quirk_maybe(q.fm, q.qx), 0)) {
-      uint32_t in[16], out[16];
+      // volatile: word-by-word local stores.  128-bit ones would force the operands and results of every squaring
+      // into aligned register quads on the HOT path (consecutive registers = alternating banks, sass_recolor.py)
+      volatile uint32_t in[16], out[16];
 #pragma unroll
       for (int i = 0; i < 8; i++) { in[i] = a.v[i]; in[8 + i] = b.v[i]; out[i] = ra.v[i]; out[8 + i] = rb.v[i]; }
-      if (fp_quirk_fix(out, in, 2)) {
+      if (fp_quirk_fix(const_cast<uint32_t*>(out), const_cast<const uint32_t*>(in), 2)) {
 #pragma unroll
         for (int i = 0; i < 8; i++) { ra.v[i] = out[i]; rb.v[i] = out[8 + i]; }
       }
@@ -504,13 +512,13 @@ template <bool QUIRK>
 __device__ __forceinline__ void fp_quirk_check(Lazy&, const QuirkAcc& q, const fe& a, fe& ra, const fe& b, fe& rb, const fe& c, fe& rc) {
   if (QUIRK) {
     if (__builtin_expect(fp_quirk_maybe(q.fm, q.qx), 0)) {
-      uint32_t in[24], out[24];
+      volatile uint32_t in[24], out[24];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         in[i] = a.v[i]; in[8 + i] = b.v[i]; in[16 + i] = c.v[i];
         out[i] = ra.v[i]; out[8 + i] = rb.v[i]; out[16 + i] = rc.v[i];
       }
-      if (fp_quirk_fix(out, in, 3)) {
+      if (fp_quirk_fix(const_cast<uint32_t*>(out), const_cast<const uint32_t*>(in), 3)) {
 #pragma unroll
         for (int i = 0; i < 8; i++) { ra.v[i] = out[i]; rb.v[i] = out[8 + i]; rc.v[i] = out[16 + i]; }
       }
