@@ -47,8 +47,9 @@ def regenerate():
 # Kernels whose registers are re-coloured after ptxas (csrc/sass_recolor.py: IMAD.WIDE multiplicands and ALU sources
 # moved to different register banks; no instruction is added, removed or moved).  ECB200_RECOLOR=0 builds without the
 # pass, ECB200_RECOLOR=strict makes a failure of the pass fatal (default: ship the kernels as ptxas wrote them and
-# say so in recolor_report.json).
-RECOLOR = {"kernels_point.cu": "k_scalar_mult_sync"}
+# say so in recolor_report.json), ECB200_RECOLOR=search ignores csrc/recolor_plans.json (the patches found for the
+# committed sources, replayed when ptxas' output matches their hash) and searches again.
+RECOLOR = {"kernels_point.cu": ("k_scalar_mult_sync", "k_pointI", "k_to_affine", "k_from_x")}
 RECOLOR_PLAN = os.path.join(CSRC, "recolor_plans.json")
 RECOLOR_REPORT = os.path.join(HERE, "recolor_report.json")
 
@@ -88,7 +89,8 @@ def _compile_recolored(nvcc, src, obj, substr, verbose):
             try:
                 import sass_recolor
                 tmp = cubin + ".recolored"
-                report = sass_recolor.recolour_cubin(cubin, tmp, substr, plan_path=RECOLOR_PLAN, verbose=verbose)
+                report = sass_recolor.recolour_cubin(cubin, tmp, substr, plan_path=RECOLOR_PLAN, verbose=verbose,
+                                                     use_plans=os.environ.get("ECB200_RECOLOR") != "search")
                 os.replace(tmp, cubin)
             except Exception as e:
                 if os.environ.get("ECB200_RECOLOR") == "strict":

@@ -678,29 +678,56 @@ def analyse(ins, verbose=False):
 # ----------------------------------------------------------------------------------------------------------------
 # hot loop and cost
 
+def _branch_target(i):
+    return int(re.search(r"(0x[0-9a-f]+)\s*$", i.text).group(1), 16) // 16
+
+
 def hot_range(ins):
-    """[lo, hi] instruction indices of the largest backward branch that encloses a BAR.SYNC (the lockstep ladder loop)."""
+    """[lo, hi] instruction indices of the largest backward branch that encloses a BAR.SYNC (the lockstep ladder loop),
+    or None"""
     bars = [i.idx for i in ins if i.op.startswith("BAR")]
     best = None
     for i in ins:
         if i.op.split(".")[0] == "BRA":
-            m = re.search(r"(0x[0-9a-f]+)\s*$", i.text)
-            t = int(m.group(1), 16) // 16
+            t = _branch_target(i)
             if t < i.idx and any(t <= b <= i.idx for b in bars):
                 if best is None or i.idx - t > best[1] - best[0]:
                     best = (t, i.idx)
     return best
 
 
-def mark_hot(ins, rng):
-    """hot = the loop minus its rare-case blocks: a forward predicated branch that jumps over a CALL skips a block
-    that only runs for a squaring-defect candidate or a 2^-32 corner case (same rule as tools/sass_census.py)."""
-    lo, hi = rng
+def mark_hot(ins, rng, calls=()):
+    """Which instructions the cost function looks at.
+      * a ladder kernel: the lockstep loop `rng`;
+      * any other kernel: the loops of the kernel body (the square-and-multiply chains of to_affine / from_x), or the
+        whole body if it has none (the straight-line point kernels) -- never the out-of-line procedures, which only
+        run for flagged lanes;
+    minus the rare-case blocks in both cases: a forward predicated branch that jumps over a CALL skips a block that
+    only runs for a squaring-defect candidate or a 2^-32 corner case (same rule as tools/sass_census.py)."""
+    callee = set()
+    for c in calls:
+        callee |= c[3]
     for i in ins:
-        i.hot = lo <= i.idx <= hi
-    for i in ins[lo:hi + 1]:
-        if i.op.split(".")[0] == "BRA" and i.guard is not None:
-            t = int(re.search(r"(0x[0-9a-f]+)\s*$", i.text).group(1), 16) // 16
+        i.hot = False
+    if rng is not None:
+        regions = [rng]
+    else:
+        regions = []
+        for i in ins:
+            if i.op.split(".")[0] == "BRA" and i.idx not in callee:
+                t = _branch_target(i)
+                if t < i.idx:
+                    regions.append((t, i.idx))
+        if not regions:
+            last = max(i.idx for i in ins if i.op not in ("NOP",) and not (i.op == "BRA" and _branch_target(i) == i.idx))
+            regions = [(0, last)]
+    for lo, hi in regions:
+        for i in ins[lo:hi + 1]:
+            if i.idx not in callee:
+                i.hot = True
+    for i in ins:
+        if i.hot and i.op.split(".")[0] == "BRA" and i.guard is not None:
+            t = _branch_target(i)
             if t > i.idx and any(j.op.startswith("CALL") for j in ins[i.idx + 1:t]):
                 for j in ins[i.idx + 1:t]:
                     j.hot = False
@@ -993,39 +1020,34 @@ def kernel_hash(ins):
     return h.hexdigest()
 
 
-def _pack_col(col):
+def _pack(b):
     import base64, zlib
-    return base64.b64encode(zlib.compress(bytes(col), 9)).decode()
+    return base64.b64encode(zlib.compress(bytes(b), 9)).decode()
 
 
-def _unpack_col(txt):
+def _unpack(txt):
     import base64, zlib
-    return list(zlib.decompress(base64.b64decode(txt)))
+    return zlib.decompress(base64.b64decode(txt))
 
 
-def recolour_section(inp, section, plan=None, iters=30000, seed=1, verbose=False, time_limit=None, weights=None):
-    """Re-colour one kernel of the cubin `inp`; returns the patched bytes of its .text section and the statistics.
-    The patched code is checked twice before it is returned: its disassembly must be the original text with the
-    renaming applied, and an independent analysis of the patched kernel must find a proper allocation."""
+def code_hash(code):
+    return hashlib.sha256(bytes(code)).hexdigest()
+
+
+def recolour_section(inp, section, iters=30000, seed=1, verbose=False, time_limit=None, weights=None):
+    """Search a re-colouring of one kernel of the cubin `inp`; returns the patched bytes of its .text section and the
+    statistics.  The patched code is checked twice before it is returned: its disassembly must be the original text
+    with the renaming applied, and an independent analysis of the patched kernel must find a proper allocation."""
     blob = open(inp, "rb").read()
     sec, off, ins = disassemble(inp, blob, section[len(".text."):], exact=True)
     A = analyse(ins, verbose)
     rng = hot_range(ins)
-    assert rng, "no lockstep loop found in %s" % sec
-    nh = mark_hot(ins, rng)
+    nh = mark_hot(ins, rng, A.calls)
     if verbose:
-        print("%s: hot loop %04x..%04x, %d hot instructions" % (sec, ins[rng[0]].addr, ins[rng[1]].addr, nh), file=sys.stderr)
-    key = kernel_hash(ins)
-    sites = pair_sites(ins, A, weights)
+        print("%s: %s, %d hot instructions" % (sec, "lockstep loop %04x..%04x" % (ins[rng[0]].addr, ins[rng[1]].addr) if rng else "no lockstep loop", nh), file=sys.stderr)
     allk = pair_sites(ins, A, {"wide": 1, "wide_rz": 1, "alu2": 1, "alu3": 1})
     col0 = [w["reg"] for w in A.webs]
-    replayed = False
-    if plan is not None and plan.get("key") == key and len(_unpack_col(plan["col"])) == len(A.webs):
-        col = _unpack_col(plan["col"])
-        start, end = cost(sites, col0), cost(sites, col)
-        replayed = True
-    else:
-        col, start, end = search(ins, A, iters, seed, verbose, time_limit, weights)
+    col, start, end = search(ins, A, iters, seed, verbose, time_limit, weights)
     for a in range(len(A.webs)):
         for b in A.adj[a]:
             assert col[a] != col[b], "colouring broken"
@@ -1039,7 +1061,7 @@ def recolour_section(inp, section, plan=None, iters=30000, seed=1, verbose=False
     finally:
         os.unlink(tmp)
     size = len(ins) * 16
-    return {"section": sec, "offset": off, "code": new[off:off + size], "key": key, "col": _pack_col(col), "replayed": replayed,
+    return {"section": sec, "offset": off, "code": new[off:off + size], "replayed": False,
             "cost_before": start, "cost_after": end, "fields_changed": changed, "hot_instructions": nh,
             "census_before": census(allk, col0), "census_after": census(allk, col)}
 
@@ -1052,33 +1074,57 @@ def _worker(args):
         return {"section": args[1], "error": "%s\n%s" % (e, traceback.format_exc())}
 
 
-def recolour_cubin(inp, outp, substr, plan_path=None, iters=30000, seed=1, jobs=None, verbose=False, weights=None):
-    """Re-colour every kernel whose .text section name contains `substr`.  plan_path: JSON {section: {key, col, ...}}
-    of colourings found earlier; a kernel whose code hash matches is replayed (seconds), the others are searched and
+def recolour_cubin(inp, outp, substr, plan_path=None, iters=30000, seed=1, jobs=None, verbose=False, weights=None, use_plans=True):
+    """Re-colour every kernel whose .text section name contains (one of) `substr`.
+
+    plan_path: JSON {section: {key, patched_key, xor, ...}} of the re-colourings found (and fully verified) earlier: `key`
+    is the SHA-256 of the kernel's code as ptxas wrote it, `xor` the byte difference to the re-coloured code and
+    `patched_key` the SHA-256 of the result.  A kernel whose code matches `key` is patched by replaying `xor` -- no
+    analysis, a few milliseconds, bit-reproducible builds; any other kernel is analysed and searched (minutes) and
     the file is updated."""
     import multiprocessing
     blob = open(inp, "rb").read()
-    secs = sorted(n for n in elf_sections(blob) if n.startswith(".text.") and substr in n)
-    assert secs, "no kernel matches %r" % substr
+    subs = [substr] if isinstance(substr, str) else list(substr)
+    elf = elf_sections(blob)
+    secs = sorted(n for n in elf if n.startswith(".text.") and any(x in n for x in subs))
+    assert secs, "no kernel matches %r" % (substr,)
     plans = json.load(open(plan_path)) if plan_path and os.path.exists(plan_path) else {}
-    work = [(inp, sec, plans.get(sec), iters, seed, verbose, None, weights) for sec in secs]
-    jobs = jobs or min(len(work), os.cpu_count() or 1)
-    if jobs > 1:
-        with multiprocessing.Pool(jobs) as pool:
-            results = pool.map(_worker, work, chunksize=1)
-    else:
-        results = [_worker(w) for w in work]
     out = bytearray(blob)
-    report = []
-    for r in results:
-        if "error" in r:
-            raise RuntimeError("sass_recolor failed on %s: %s" % (r["section"], r["error"]))
-        out[r["offset"]:r["offset"] + len(r["code"])] = r["code"]
-        plans[r["section"]] = {k: r[k] for k in ("key", "col", "cost_before", "cost_after", "census_before", "census_after")}
-        report.append({k: v for k, v in r.items() if k not in ("code", "col")})
+    report, work = [], []
+    for sec in secs:
+        off, size, _ = elf[sec]
+        code = blob[off:off + size]
+        pl = plans.get(sec) if use_plans else None
+        if pl is not None and pl.get("key") == code_hash(code):
+            x = _unpack(pl["xor"])
+            assert len(x) == size
+            patched = bytes(a ^ b for a, b in zip(code, x))
+            assert code_hash(patched) == pl["patched_key"], "stored patch of %s does not reproduce its own hash" % sec
+            out[off:off + size] = patched
+            report.append({"section": sec, "replayed": True, **{k: pl[k] for k in ("cost_before", "cost_after", "hot_instructions", "census_before", "census_after") if k in pl}})
+        else:
+            work.append((inp, sec, iters, seed, verbose, None, weights))
+    if work:
+        jobs = jobs or min(len(work), os.cpu_count() or 1)
+        if jobs > 1:
+            with multiprocessing.Pool(jobs) as pool:
+                results = pool.map(_worker, work, chunksize=1)
+        else:
+            results = [_worker(w) for w in work]
+        for r in results:
+            if "error" in r:
+                raise RuntimeError("sass_recolor failed on %s: %s" % (r["section"], r["error"]))
+            off, size, _ = elf[r["section"]]
+            assert off == r["offset"] and size == len(r["code"])
+            code = blob[off:off + size]
+            out[off:off + size] = r["code"]
+            plans[r["section"]] = {"key": code_hash(code), "patched_key": code_hash(r["code"]),
+                                   "xor": _pack(bytes(a ^ b for a, b in zip(code, r["code"]))),
+                                   **{k: r[k] for k in ("cost_before", "cost_after", "hot_instructions", "census_before", "census_after")}}
+            report.append({k: v for k, v in r.items() if k != "code"})
+        if plan_path:
+            json.dump(plans, open(plan_path, "w"), indent=0, sort_keys=True)
     open(outp, "wb").write(bytes(out))
-    if plan_path and not all(r["replayed"] for r in results):
-        json.dump(plans, open(plan_path, "w"), indent=0, sort_keys=True)
     return report
 
 
@@ -1097,7 +1143,7 @@ def main():
     w = None
     if a.weights:
         w = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.weights.split(",")}
-    for r in recolour_cubin(a.inp, a.out, a.kernel, a.plan, a.iters, a.seed, a.jobs, a.v, w):
+    for r in recolour_cubin(a.inp, a.out, a.kernel.split(","), a.plan, a.iters, a.seed, a.jobs, a.v, w):
         print(json.dumps(r))
 
 
