@@ -375,7 +375,7 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops, fresh_hook=None):
                 lo, hi = R(acc, w), R(acc, w + 1)
                 last = n == len(ch) - 1
                 fresh = (lo not in touched, hi not in touched)
-                if allfresh and not (n == 0 and w == 0):
+                if allfresh and not (n == 0 and w == 0 and not MULW_WORD0):
                     g.mulw(lo, hi, xa % i, xb % j)
                 elif allfresh:
                     # word 0 of the product is m_0, read four more times by the reduction: written as a
@@ -403,6 +403,7 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops, fresh_hook=None):
 
 
 PIN_M0 = True
+MULW_WORD0 = True   # a_0*b_0 as mul.wide like the other first products: the m_0 pin below then costs one ALU add instead of an IMAD
 
 
 def emit_reduction(g, T):
@@ -556,8 +557,11 @@ def gen_sqr():
         g.shf_l("d%d" % w, "s%d" % (w - 1), "s%d" % w, 1)
     g.end()
     # T = d + sum a_i^2 2^(64 i): one chain of eight multiply-adds on the pairs (2i, 2i+1)
+    # a_0^2 as a fresh 64-bit product whose high word is then added to d1: as a multiply-add onto (nothing, d1) ptxas
+    # splits it into IMAD + IMAD.HI (2 + 5.1 issue clocks instead of 4.1 + 1.2)
     g.begin()
-    g.madw("t0", "d1", "a0", "a0", False, True, fresh=(True, False))
+    g.mulw("t0", "x1", "a0", "a0")
+    g.add32("d1", "d1", "x1", False, True)
     for i in range(1, 8):
         g.madw("d%d" % (2 * i), "d%d" % (2 * i + 1), "a%d" % i, "a%d" % i, True, i < 7)
     g.end()

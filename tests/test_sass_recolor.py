@@ -1,0 +1,149 @@
+"""The post-ptxas register re-colouring pass (ecsimd_b200/csrc/sass_recolor.py) on the CPU: no GPU is needed to
+check that a re-coloured kernel is the same program -- the pass itself verifies that (1) the patched code
+disassembles to the original text with the renaming applied, instruction by instruction, that (2) nothing but
+register fields changed and that (3) an independent liveness analysis of the patched code still finds a proper
+register allocation; these tests drive it on a small kernel built from the real field arithmetic (lockstep loop,
+IMAD.WIDE chains, the squaring-defect cold path with its out-of-line calls) and pin the properties of the plan file
+the build replays.  What the kernels COMPUTE after re-colouring is the business of the `-m gpu` parity tests, which
+run the re-coloured library against the oracle."""
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "ecsimd_b200", "csrc")
+sys.path.insert(0, CSRC)
+import sass_recolor as rc  # noqa: E402
+
+needs_nvcc = pytest.mark.skipif(shutil.which("nvcc") is None or shutil.which("nvdisasm") is None, reason="CUDA toolkit not on PATH")
+
+SMALL_TU = r'''
+#include "fp256.cuh"
+using namespace ecb200;
+// a miniature of the ladder loop: lockstep block, multiply + two grouped squarings with their defect check per trip
+extern "C" __global__ void __launch_bounds__(256, 1) k_small(uint32_t* out, const uint32_t* in, int steps) {
+  fe a, b;
+  for (int i = 0; i < 8; i++) { a.v[i] = in[(threadIdx.x * 16 + i)]; b.v[i] = in[threadIdx.x * 16 + 8 + i]; }
+  Lazy md;
+#pragma unroll 1
+  for (int s = 0; s < steps; s++) {
+    QuirkAcc q;
+    const fe d = fp_sub(a, b);
+    fe s1 = fp_sqr_acc<true>(d, md, q);
+    fe s2 = fp_sqr_acc<true>(a, md, q);
+    fp_quirk_check<true>(md, q, d, s1, a, s2);
+    const fe m = fp_mul(s1, b, md);
+    a = fp_add(m, s2, md);
+    b = fp_sub(s2, d);
+    __syncthreads();
+  }
+  for (int i = 0; i < 8; i++) { out[threadIdx.x * 16 + i] = a.v[i]; out[threadIdx.x * 16 + 8 + i] = b.v[i] ^ md.top; }
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def small_cubin(tmp_path_factory):
+    d = tmp_path_factory.mktemp("recolor")
+    cu = d / "small.cu"
+    cu.write_text(SMALL_TU)
+    cubin = d / "small.cubin"
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-diag-suppress", "550", "-I", CSRC,
+                    "-cubin", "-o", str(cubin), str(cu)], check=True)
+    return str(cubin)
+
+
+@needs_nvcc
+def test_recolour_small_kernel_is_verified_and_improves(small_cubin, tmp_path):
+    out = str(tmp_path / "out.cubin")
+    plan = str(tmp_path / "plan.json")
+    rep = rc.recolour_cubin(small_cubin, out, "k_small", plan_path=plan, iters=1500, jobs=1)
+    assert len(rep) == 1 and not rep[0]["replayed"]
+    r = rep[0]
+    assert r["fields_changed"] > 0 and r["cost_after"] < r["cost_before"]
+    assert r["census_after"].get("wide_same", 0) < r["census_before"]["wide_same"]
+    a, b = open(small_cubin, "rb").read(), open(out, "rb").read()
+    secs = rc.elf_sections(a)
+    off, size, _ = secs[".text.k_small"]
+    assert len(a) == len(b) and a[:off] == b[:off] and a[off + size:] == b[off + size:]      # only that kernel's code changed
+    # every changed bit lies in a register field (bits 16..39 of the low word, 0..7 of the high word)
+    for k in range(off, off + size, 16):
+        la, ha = int.from_bytes(a[k:k + 8], "little"), int.from_bytes(a[k + 8:k + 16], "little")
+        lb, hb = int.from_bytes(b[k:k + 8], "little"), int.from_bytes(b[k + 8:k + 16], "little")
+        assert (la ^ lb) & ~(0xFFFFFF << 16) == 0 and (ha ^ hb) & ~0xFF == 0
+    # replaying the plan reproduces the same bytes without any analysis
+    out2 = str(tmp_path / "out2.cubin")
+    rep2 = rc.recolour_cubin(small_cubin, out2, "k_small", plan_path=plan, jobs=1)
+    assert rep2[0]["replayed"] and open(out2, "rb").read() == b
+
+
+@needs_nvcc
+def test_analysis_models_calls_and_barriers(small_cubin):
+    blob = open(small_cubin, "rb").read()
+    sec, off, ins = rc.disassemble(small_cubin, blob, "k_small")
+    A = rc.analyse(ins)
+    assert A.calls, "the cold path's out-of-line call is part of the kernel"
+    rng = rc.hot_range(ins)
+    assert rng is not None
+    n_hot = rc.mark_hot(ins, rng, A.calls)
+    assert 300 < n_hot < rng[1] - rng[0] + 1          # the loop minus its rare-case blocks
+    # the allocation ptxas chose is a proper colouring of the interference graph this pass builds, and tied webs
+    # (register pairs of IMAD.WIDE, 64/128-bit memory operands) sit on aligned consecutive registers
+    for w, web in enumerate(A.webs):
+        assert all(A.webs[o]["reg"] != web["reg"] for o in A.adj[w])
+    for g, members in enumerate(A.groups):
+        if A.align[g] > 1:
+            base = min(A.webs[w]["reg"] for w in members)
+            assert base % 2 == 0
+    # a Kempe move never produces an improper colouring
+    C = rc.Colouring(A)
+    import random
+    rnd = random.Random(7)
+    moved = 0
+    singles = [w for w in range(len(A.webs)) if A.align[A.group_of[w]] == 1 and A.group_of[w] not in C.pinned and A.webs[w]["occ"]]
+    for _ in range(300):
+        w = rnd.choice(singles)
+        c2 = rnd.randrange(0, C.maxreg + 1)
+        if c2 in (1, C.col[w]):
+            continue
+        mv = C.kempe(A.group_of[w], c2 - C.col[w])
+        if mv is None:
+            continue
+        for ww, cc in mv[1].items():
+            C.col[ww] = cc
+        moved += 1
+    assert moved > 20
+    for w in range(len(A.webs)):
+        assert all(C.col[o] != C.col[w] for o in A.adj[w])
+        assert C.col[w] != 1 or A.webs[w]["reg"] == 1      # the stack pointer keeps R1 to itself
+
+
+def test_plan_file_is_consistent():
+    """csrc/recolor_plans.json: one verified patch per re-coloured kernel, each reproducing its own hash"""
+    path = os.path.join(CSRC, "recolor_plans.json")
+    plans = json.load(open(path))
+    assert sum(1 for s in plans if "k_scalar_mult_sync" in s) == 12
+    for sec, pl in plans.items():
+        x = rc._unpack(pl["xor"])
+        assert len(x) % 16 == 0 and any(x)
+        for k in range(0, len(x), 16):          # patches touch register fields only
+            lo, hi = int.from_bytes(x[k:k + 8], "little"), int.from_bytes(x[k + 8:k + 16], "little")
+            assert lo & ~(0xFFFFFF << 16) == 0 and hi & ~0xFF == 0, sec
+        assert pl["cost_after"] <= pl["cost_before"]
+        assert len(pl["key"]) == 64 and len(pl["patched_key"]) == 64 and pl["key"] != pl["patched_key"]
+
+
+def test_build_report_says_what_was_shipped():
+    """if the library was built here, its report names every re-coloured kernel and no failure"""
+    rep = os.path.join(ROOT, "ecsimd_b200", "recolor_report.json")
+    lib = os.path.join(ROOT, "ecsimd_b200", "libecb200.so")
+    if not (os.path.exists(rep) and os.path.exists(lib)):
+        pytest.skip("library not built with the re-colouring pass in this checkout")
+    r = json.load(open(rep))
+    assert isinstance(r["kernels"], list), "the pass failed at build time: %r" % (r["kernels"],)
+    assert sum(1 for k in r["kernels"] if "k_scalar_mult_sync" in k["section"]) == 12
