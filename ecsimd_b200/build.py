@@ -88,6 +88,7 @@ def _compile_recolored(nvcc, src, obj, substr, verbose):
             sys.path.insert(0, CSRC)
             try:
                 import sass_recolor
+                shutil.copyfile(cubin, cubin + ".orig")          # what ptxas wrote (tools/recolor_autotune.py starts from it)
                 tmp = cubin + ".recolored"
                 report = sass_recolor.recolour_cubin(cubin, tmp, substr, plan_path=RECOLOR_PLAN, verbose=verbose,
                                                      use_plans=os.environ.get("ECB200_RECOLOR") != "search")

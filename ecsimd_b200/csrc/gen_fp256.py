@@ -403,7 +403,7 @@ def emit_products(g, chains_e, chains_o, xa, xb, tops, fresh_hook=None):
 
 
 PIN_M0 = True
-MULW_WORD0 = True   # a_0*b_0 as mul.wide like the other first products: the m_0 pin below then costs one ALU add instead of an IMAD
+MULW_WORD0 = False  # True: a_0*b_0 as mul.wide too (the m_0 pin then costs one ALU add instead of an IMAD): no gain in the ladder, -4.7 % on the register-resident multiply chain (ptxas schedules it worse)
 
 
 def emit_reduction(g, T):

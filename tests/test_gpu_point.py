@@ -269,3 +269,37 @@ def test_from_x(eng, orc, pts):
     ys, ya = _libs.to_ints(y[good]), _libs.to_ints(aff[good, 8:])
     assert all(a == b or a == _libs.P_INT - b for a, b in zip(ys, ya))
     assert _libs.to_ints(eng.from_x(to_words([GX_INT]))[0])[0] in (GY_INT, _libs.P_INT - GY_INT)
+
+
+def test_every_ladder_instance_is_repeatable_at_full_occupancy(eng, orc):
+    """Each shipped instance of the ladder kernel (3 layouts x variable base / fixed base from the table / fixed base
+    plain, + the NO_QUIRK planar ones) on more than two full waves, three times: identical outputs every time and
+    equal to the oracle on sampled lanes.  A kernel that is correct on a few hundred lanes can still be wrong when all
+    148 SMs run 16 warps each (a re-coloured kernel whose register renaming ignored a pending scoreboard computed
+    timing-dependent garbage in exactly one of these instances)."""
+    n = 2 * 148 * 512 + 512 * 3 + 8
+    k = raw256(0xEC51D011, n)
+    G = np.concatenate([to_words([GX_INT]), to_words([GY_INT])], axis=1)
+    idx = np.unique(np.concatenate([np.arange(96), np.arange(n - 96, n), np.arange(0, n, 1531)]))
+    P = _points(orc, 64, 0xEC51D012)[np.arange(n) % 64]
+    want_var = orc.scalar_mult(k[idx], P[idx])
+    want_base = orc.scalar_mult(k[idx], orc.from_affine(np.repeat(G, len(idx), axis=0)))
+    conv = {"lane": (lambda x, nc: x, lambda x, nc: x), "pack4": (eng.lane_to_pack4, eng.pack4_to_lane),
+            "soa": (eng.lane_to_soa, eng.soa_to_lane)}
+    for layout, (to, back) in conv.items():
+        kl, Pl = to(k, 1), to(P, 3)
+        runs = {
+            "variable": (lambda: eng.scalar_mult(kl, Pl, layout=layout), want_var),
+            "table": (lambda: eng.scalar_mult_base(kl, layout=layout, table=True), want_base),
+            "plain": (lambda: eng.scalar_mult_base(kl, layout=layout, table=False), want_base),
+        }
+        if layout == "soa":
+            runs["variable, no quirk"] = (lambda: eng.scalar_mult(kl, Pl, layout=layout, quirk=False), None)
+            runs["table, no quirk"] = (lambda: eng.scalar_mult_base(kl, layout=layout, quirk=False, table=True), None)
+            runs["plain, no quirk"] = (lambda: eng.scalar_mult_base(kl, layout=layout, quirk=False, table=False), None)
+        for name, (run, want) in runs.items():
+            first = run()
+            for rep in range(2):
+                assert np.array_equal(run(), first), "%s %s: run %d differs from the first" % (layout, name, rep + 2)
+            if want is not None:
+                assert np.array_equal(back(first, 3)[idx], want), "%s %s vs oracle" % (layout, name)

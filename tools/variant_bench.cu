@@ -5,6 +5,9 @@
 // between variants that compute the same thing.
 // Build: nvcc -O2 -std=c++17 -o build/variant_bench tools/variant_bench.cu -lcuda
 // Run:   build/variant_bench <log2 lanes> a.cubin b.cubin ...
+// With KERNEL=<mangled name> in the environment the cubins are variants of the library's own translation unit
+// (kernels_point.cubin) and that instance of k_scalar_mult_sync is launched (out, k, P, n, k_bcast = 0, tab = NULL):
+// tools/recolor_autotune.py times several re-colourings of a shipped kernel this way.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +36,8 @@ int main(int argc, char** argv) {
   for (int a = 2; a < argc; a++) {
     CUmodule mod;
     if (cuModuleLoad(&mod, argv[a]) != CUDA_SUCCESS) { printf("{\"variant\": \"%s\", \"error\": \"load\"}\n", argv[a]); continue; }
-    CUfunction fn; CK(cuModuleGetFunction(&fn, mod, "k_ladder"));
+    const char* kname = getenv("KERNEL");
+    CUfunction fn; CK(cuModuleGetFunction(&fn, mod, kname ? kname : "k_ladder"));
     int threads = 512;
     CK(cuFuncGetAttribute(&threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, fn));
     if (threads > 512) threads = 512;
@@ -41,7 +45,17 @@ int main(int argc, char** argv) {
     const unsigned smem = 5 * 2 * 512 * 16;   // LadderSmem<512>::kBytes (unused by the register-state variants)
     CK(cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem));
     size_t nn = n;
-    void* args[] = {&dout, &dk, &dP, &nn};
+    int k_bcast = 0;
+    CUdeviceptr tab = 0;
+    if (const char* tk = getenv("TABLE_KERNEL")) {   // fixed-base instance: build the 2^16-entry table with the module's own kernel
+      CUfunction tf; CK(cuModuleGetFunction(&tf, mod, tk));
+      CK(cuMemAlloc(&tab, (size_t)160 << 16));
+      int tabw = 16;
+      void* targs[] = {&tab, &tabw};
+      CK(cuLaunchKernel(tf, (1u << 16) / 128, 1, 1, 128, 1, 1, 0, 0, targs, 0));
+      CK(cuCtxSynchronize());
+    }
+    void* args[] = {&dout, &dk, &dP, &nn, &k_bcast, &tab};   // the stand-alone k_ladder takes the first four
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     CK(cuMemsetD8(dout, 0, n * 96));
     CK(cuLaunchKernel(fn, blocks, 1, 1, threads, 1, 1, smem, 0, args, 0));
@@ -56,11 +70,20 @@ int main(int argc, char** argv) {
       if (ms < best) best = ms;
     }
     std::vector<uint32_t> o(n * 24);
-    CK(cuMemcpyDtoH(o.data(), dout, n * 96));
     uint64_t sum = 0;
-    for (size_t i = 0; i < o.size(); i++) sum = sum * 1099511628211ull + o[i];
-    printf("{\"variant\": \"%s\", \"lanes\": %zu, \"threads\": %d, \"regs\": %d, \"ms\": %.4f, \"Mps\": %.3f, \"checksum\": \"%016llx\"}\n", argv[a], n, threads, regs, best,
-           n / best * 1e-3, (unsigned long long)sum);
+    int unstable = 0;   // REPEAT=<r> in the environment: r more runs whose outputs must all have the same checksum
+    const int repeat = getenv("REPEAT") ? atoi(getenv("REPEAT")) : 0;
+    for (int rep = 0; rep <= repeat; rep++) {
+      if (rep) { CK(cuLaunchKernel(fn, blocks, 1, 1, threads, 1, 1, smem, 0, args, 0)); }
+      CK(cuMemcpyDtoH(o.data(), dout, n * 96));
+      uint64_t s2 = 0;
+      for (size_t i = 0; i < o.size(); i++) s2 = s2 * 1099511628211ull + o[i];
+      if (rep && s2 != sum) unstable++;
+      if (!rep) sum = s2;
+    }
+    if (tab) CK(cuMemFree(tab));
+    printf("{\"variant\": \"%s\", \"lanes\": %zu, \"threads\": %d, \"regs\": %d, \"ms\": %.4f, \"Mps\": %.3f, \"checksum\": \"%016llx\", \"unstable_runs\": %d}\n", argv[a], n, threads, regs, best,
+           n / best * 1e-3, (unsigned long long)sum, unstable);
     fflush(stdout);
     CK(cuModuleUnload(mod));
   }
