@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Differential fuzz of the GPU engine against the CPU oracle on EVERY lane (not sampled): random scalars and
 points (a share of them out-of-contract bit patterns), all three layouts, variable base / generator / fused
-affine.  usage: fuzz_vs_oracle.py [seeds] [lanes]"""
+affine.  usage: fuzz_vs_oracle.py [seeds] [lanes]
+Use at least 9 seeds (3 layouts x 3 fixed-base layouts) and more than 2 x 148 x 512 lanes: a kernel can be right on a
+partly filled GPU and wrong at full occupancy (profiles/r2e_recolor_bug/README.md)."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,10 +35,14 @@ for s in range(seeds):
     got = conv[1](eng.scalar_mult(conv[0](k, 1), conv[0](P, 3), layout=layout), 3)
     e1 = int((got != want).any(axis=1).sum())
     wantg = orc.scalar_mult(k, GJ)
-    e2 = int((eng.scalar_mult_base(k) != wantg).any(axis=1).sum())
+    # fixed base: every layout's table instance and plain instance over the seeds (each is its own kernel)
+    blayout = ("lane", "pack4", "soa")[(s // 3) % 3]
+    bconv = {"lane": (lambda x, nc: x, lambda x, nc: x), "pack4": (eng.lane_to_pack4, eng.pack4_to_lane), "soa": (eng.lane_to_soa, eng.soa_to_lane)}[blayout]
+    e2 = int((bconv[1](eng.scalar_mult_base(bconv[0](k, 1), layout=blayout, table=True), 3) != wantg).any(axis=1).sum())
+    e2 += int((bconv[1](eng.scalar_mult_base(bconv[0](k, 1), layout=blayout, table=False), 3) != wantg).any(axis=1).sum())
     e3 = int((eng.scalar_mult_affine(k, P) != orc.to_affine(want)).any(axis=1).sum())
     e4 = int((eng.mgry_sqr(P[:, :8]) != orc.mgry_sqr(P[:, :8])).any(axis=1).sum()) + int((eng.mgry_mul(P[:, :8], P[:, 8:16]) != orc.mgry_mul(P[:, :8], P[:, 8:16])).any(axis=1).sum())
     bad += e1 + e2 + e3 + e4
-    print({"seed": s, "layout": layout, "lanes": n, "mismatch_var": e1, "mismatch_base": e2, "mismatch_affine": e3, "mismatch_field": e4}, flush=True)
+    print({"seed": s, "layout": layout, "base_layout": blayout, "lanes": n, "mismatch_var": e1, "mismatch_base": e2, "mismatch_affine": e3, "mismatch_field": e4}, flush=True)
 print({"total_mismatches": bad, "seconds": round(time.time() - t0, 1)})
 sys.exit(1 if bad else 0)

@@ -303,3 +303,28 @@ def test_every_ladder_instance_is_repeatable_at_full_occupancy(eng, orc):
                 assert np.array_equal(run(), first), "%s %s: run %d differs from the first" % (layout, name, rep + 2)
             if want is not None:
                 assert np.array_equal(back(first, 3)[idx], want), "%s %s vs oracle" % (layout, name)
+
+
+def test_flagged_lanes_under_load_are_repeatable(eng, orc):
+    """Whole warps of lanes that take the out-of-line exact re-run (P = (2^256-1, 2^256-1): out of contract, every
+    conditional subtraction hits its 2^-32 case), more than two full waves, several runs: identical every time and
+    equal to the oracle.  The callee's result stores are issued without a read scoreboard of their own; a register
+    renaming that ignored that produced one wrong word in a whole warp about once in 10^4 warp-runs."""
+    n = 2 * 148 * 512 + 512
+    k = raw256(0xEC51D021, n)
+    P = np.zeros((n, 24), np.uint32)
+    P[:, :16] = 0xFFFFFFFF
+    P[:, 16:] = to_words([_libs.R_INT % _libs.P_INT])   # Z = R like every input of the reference's scalar_mult
+    good = _points(orc, 64, 0xEC51D022)
+    P[1::3] = good[np.arange(len(P[1::3])) % 64]          # a third of the lanes are ordinary points: mixed warps
+    idx = np.unique(np.concatenate([np.arange(64), np.arange(n - 64, n), np.arange(0, n, 1201)]))
+    want = orc.scalar_mult(k[idx], P[idx])
+    for layout, (to, back) in {"lane": (lambda x, nc: x, lambda x, nc: x), "pack4": (eng.lane_to_pack4, eng.pack4_to_lane),
+                               "soa": (eng.lane_to_soa, eng.soa_to_lane)}.items():
+        kl, Pl = to(k, 1), to(P, 3)
+        first = eng.scalar_mult(kl, Pl, layout=layout)
+        assert np.array_equal(back(first, 3)[idx], want), layout
+        for rep in range(5):
+            again = eng.scalar_mult(kl, Pl, layout=layout)
+            bad = np.nonzero((back(again, 3) != back(first, 3)).any(axis=1))[0]
+            assert len(bad) == 0, "%s run %d: lanes %s differ from the first run" % (layout, rep + 2, bad[:8].tolist())
