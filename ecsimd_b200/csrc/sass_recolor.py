@@ -85,7 +85,7 @@ def elf_symbol_index(blob, name):
 # disassembly
 
 class Ins:
-    __slots__ = ("idx", "addr", "text", "guard", "op", "ops", "lo", "hi", "defs", "uses", "succ", "fields", "hot")
+    __slots__ = ("idx", "addr", "text", "guard", "op", "ops", "lo", "hi", "defs", "uses", "succ", "fields", "hot", "body")
 
 
 _GUARD = re.compile(r"^@(!?U?P\d+|!?U?PT)\s+")
@@ -490,6 +490,9 @@ def control(i):
 
 
 _LSU = ("LD", "ST", "ATOM", "RED", "LDGSTS", "CCTL", "MEMBAR")
+# variable-latency whether or not an instance in this kernel happens to carry a scoreboard (e.g. the last stores before EXIT)
+_OTHER_VARIABLE = ("MUFU", "S2R", "SHFL", "I2F", "F2I", "F2F", "I2I", "POPC", "FLO", "BREV", "R2UR", "S2UR", "MATCH", "VOTE",
+                   "DADD", "DMUL", "DFMA", "DSETP", "HMMA", "IMMA", "QMMA", "TEX", "TLD", "SULD", "SUST")
 
 
 def _queue(i):
@@ -507,11 +510,13 @@ def scoreboard_shadows(ins):
     WITHOUT a read scoreboard of its own (ptxas does that for all but the last of a run of stores: `STL; STL; ...;
     STL &rd=4; RET &wait=4`) is covered by the next scoreboard set in the same in-order queue -- its registers are
     read before those of the later instruction -- and pending until that one is waited on.  Which opcodes are
-    variable-latency is learnt from the kernel: every opcode that carries a scoreboard somewhere in it.  Never
+    variable-latency: every load / store / atomic, a list of known ones, and every opcode that carries a scoreboard
+    somewhere in the kernel.  Never
     waited on = pending to the end of the kernel (conservative)."""
     n = len(ins)
     ctl = [control(i) for i in ins]
     variable = set(i.op.split(".")[0] for i, c in zip(ins, ctl) if c["rbar"] != 7 or c["wbar"] != 7)
+    variable |= set(i.op.split(".")[0] for i in ins if i.op.split(".")[0].startswith(_LSU + _OTHER_VARIABLE))
     state = [None] * n
     state[0] = frozenset()
     work = collections.deque([0])
@@ -887,6 +892,25 @@ def mark_hot(ins, rng, calls=()):
     return sum(1 for i in ins if i.hot)
 
 
+def mark_body(ins, calls=()):
+    """i.body = the instruction is executed by every thread, every time: the kernel body without its out-of-line
+    procedures and without its rare-case blocks (same rule as mark_hot).  Code that runs this often is checked by
+    every parity test at full scale; a rare-case block or an out-of-line procedure is not, so the values that live
+    there keep the registers ptxas gave them (Colouring, scope "body")."""
+    callee = set()
+    for c in calls:
+        callee |= c[3]
+    for i in ins:
+        i.body = i.idx not in callee
+    for i in ins:
+        if i.body and i.op.split(".")[0] == "BRA" and i.guard is not None:
+            t = _branch_target(i)
+            if t > i.idx and any(j.op.startswith("CALL") for j in ins[i.idx + 1:t]):
+                for j in ins[i.idx + 1:t]:
+                    j.body = False
+    return sum(1 for i in ins if i.body)
+
+
 # issue clocks per same-bank pair in the ladder loop, fitted on 34 re-colourings of the same kernel timed on a B200
 # (profiles/r2_recolor_fit.md): IMAD.WIDE multiplicands 0.39, two-source ALU instruction 0.17, three-source
 # instruction with all three in one bank 0.55 (= 0.275 per pair beyond the unavoidable one)
@@ -945,12 +969,27 @@ def census(sites, col):
 # search
 
 class Colouring:
-    def __init__(self, A, pinned_regs=(1,)):
+    def __init__(self, A, pinned_regs=(1,), ins=None, scope=None):
+        """scope = "body" (needs ins with .body set, mark_body): only values whose every definition and use is in code
+        that every thread executes every time may change register -- everything that is defined or used in a rare-case
+        block or an out-of-line procedure keeps the register ptxas gave it (a Kempe chain that reaches such a value is
+        refused).  scope = "hot": the same with the hot loop only (prologue and epilogue pinned too).
+        scope = "warm" (the default): a value may change register if at least one of its definitions or uses is a hot
+        instruction; a value that never appears in the hot loop -- all of the prologue, the epilogue, the rare-case
+        blocks' and the out-of-line procedures' own temporaries -- keeps its register, since moving it gains nothing
+        and that code is not exercised at scale by the parity tests (both timing-dependent miscompiles found in round 2
+        were collateral moves of such values).  Costs nothing: 67.5 against 66.7 cost units for "all" (no restriction)."""
         self.A = A
         self.col = [w["reg"] for w in A.webs]
         self.pinned = set()
         for w, web in enumerate(A.webs):
             if web["reg"] in pinned_regs or w in A.entry_webs:
+                self.pinned.add(A.group_of[w])
+            elif scope == "hot" and (not web["occ"] or any(not ins[k].hot for k, oi, j in web["occ"])):
+                self.pinned.add(A.group_of[w])
+            elif scope == "warm" and not any(ins[k].hot for k, oi, j in web["occ"]):
+                self.pinned.add(A.group_of[w])
+            elif scope == "body" and (not web["occ"] or any(not ins[k].body for k, oi, j in web["occ"])):
                 self.pinned.add(A.group_of[w])
         self.maxreg = max(self.col)
 
@@ -1005,11 +1044,16 @@ def cost(sites, col):
     return sum(s[0] for s in sites if (col[s[1]] ^ col[s[2]]) & 1 == 0)
 
 
+SCOPE = os.environ.get("ECB200_RECOLOR_SCOPE", "warm")      # "warm" | "body" | "hot" | "all"
+
+
 def search(ins, A, iters, seed, verbose=False, time_limit=None, weights=None, best_of=10):
     """Simulated annealing over parity-changing Kempe moves of untied webs.  Deterministic for a given (iters, seed)
     when no time limit is given.  Returns (colouring, cost before, cost after)."""
     rnd = random.Random(seed)
-    C = Colouring(A)
+    C = Colouring(A, ins=ins, scope=SCOPE)
+    if verbose:
+        print("search: scope %s, %d of %d groups pinned" % (SCOPE, len(C.pinned), len(A.groups)), file=sys.stderr)
     sites = pair_sites(ins, A, weights)
     ns = len(sites)
     site_of = collections.defaultdict(list)
@@ -1203,6 +1247,7 @@ def recolour_section(inp, section, iters=30000, seed=1, verbose=False, time_limi
     A = analyse(ins, verbose)
     rng = hot_range(ins)
     nh = mark_hot(ins, rng, A.calls)
+    mark_body(ins, A.calls)
     if verbose:
         print("%s: %s, %d hot instructions" % (sec, "lockstep loop %04x..%04x" % (ins[rng[0]].addr, ins[rng[1]].addr) if rng else "no lockstep loop", nh), file=sys.stderr)
     allk = pair_sites(ins, A, {"wide": 1, "wide_rz": 1, "alu2": 1, "alu3": 1})
