@@ -47,8 +47,10 @@ def regenerate():
 # Kernels whose registers are re-coloured after ptxas (csrc/sass_recolor.py: IMAD.WIDE multiplicands and ALU sources
 # moved to different register banks; no instruction is added, removed or moved).  ECB200_RECOLOR=0 builds without the
 # pass, ECB200_RECOLOR=strict makes a failure of the pass fatal (default: ship the kernels as ptxas wrote them and
-# say so in recolor_report.json), ECB200_RECOLOR=search ignores csrc/recolor_plans.json (the patches found for the
-# committed sources, replayed when ptxas' output matches their hash) and searches again.
+# say so in recolor_report.json).  The default build only REPLAYS csrc/recolor_plans.json (the patches found and verified for
+# the committed sources, keyed by the hash of ptxas' output: milliseconds, bit-reproducible); a kernel whose code has no
+# stored patch (another ptxas) ships as ptxas wrote it and the report says so.  ECB200_RECOLOR=auto searches the missing
+# ones (minutes per kernel), ECB200_RECOLOR=search ignores the stored patches and searches everything again.
 RECOLOR = {"kernels_point.cu": ("k_scalar_mult_sync", "k_pointI", "k_to_affine", "k_from_x")}
 RECOLOR_PLAN = os.path.join(CSRC, "recolor_plans.json")
 RECOLOR_REPORT = os.path.join(HERE, "recolor_report.json")
@@ -90,8 +92,9 @@ def _compile_recolored(nvcc, src, obj, substr, verbose):
                 import sass_recolor
                 shutil.copyfile(cubin, cubin + ".orig")          # what ptxas wrote (tools/recolor_autotune.py starts from it)
                 tmp = cubin + ".recolored"
+                mode = os.environ.get("ECB200_RECOLOR", "1")
                 report = sass_recolor.recolour_cubin(cubin, tmp, substr, plan_path=RECOLOR_PLAN, verbose=verbose,
-                                                     use_plans=os.environ.get("ECB200_RECOLOR") != "search")
+                                                     use_plans=mode != "search", search_missing=mode in ("search", "auto", "strict"))
                 os.replace(tmp, cubin)
             except Exception as e:
                 if os.environ.get("ECB200_RECOLOR") == "strict":

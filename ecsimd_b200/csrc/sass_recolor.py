@@ -1279,14 +1279,17 @@ def _worker(args):
         return {"section": args[1], "error": "%s\n%s" % (e, traceback.format_exc())}
 
 
-def recolour_cubin(inp, outp, substr, plan_path=None, iters=30000, seed=1, jobs=None, verbose=False, weights=None, use_plans=True):
+def recolour_cubin(inp, outp, substr, plan_path=None, iters=30000, seed=1, jobs=None, verbose=False, weights=None, use_plans=True,
+                   search_missing=True):
     """Re-colour every kernel whose .text section name contains (one of) `substr`.
 
     plan_path: JSON {section: {key, patched_key, xor, ...}} of the re-colourings found (and fully verified) earlier: `key`
     is the SHA-256 of the kernel's code as ptxas wrote it, `xor` the byte difference to the re-coloured code and
     `patched_key` the SHA-256 of the result.  A kernel whose code matches `key` is patched by replaying `xor` -- no
     analysis, a few milliseconds, bit-reproducible builds; any other kernel is analysed and searched (minutes) and
-    the file is updated."""
+    the file is updated -- unless search_missing is False (the default of the library build: an unattended build
+    must not turn into a ten-minute search because a toolchain update changed ptxas' output), in which case it is
+    left as ptxas wrote it and reported as such."""
     import multiprocessing
     blob = open(inp, "rb").read()
     subs = [substr] if isinstance(substr, str) else list(substr)
@@ -1307,8 +1310,10 @@ def recolour_cubin(inp, outp, substr, plan_path=None, iters=30000, seed=1, jobs=
             assert code_hash(patched) == pl["patched_key"], "stored patch of %s does not reproduce its own hash" % sec
             out[off:off + size] = patched
             report.append({"section": sec, "replayed": True, **{k: pl[k] for k in ("cost_before", "cost_after", "hot_instructions", "census_before", "census_after") if k in pl}})
-        else:
+        elif search_missing or not use_plans:
             work.append((inp, sec, iters, seed, verbose, None, weights))
+        else:          # replay-only build: a kernel whose code has no stored patch ships as ptxas wrote it
+            report.append({"section": sec, "replayed": False, "unpatched": "no stored patch for this code (ECB200_RECOLOR=auto searches one)"})
     if work:
         jobs = jobs or min(len(work), os.cpu_count() or 1)
         if jobs > 1:
