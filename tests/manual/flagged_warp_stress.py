@@ -1,5 +1,8 @@
+#!/usr/bin/env python3
+"""Repeats the differential-fuzz inputs whose lanes take the out-of-line exact re-run (see README.md here and
+profiles/r2e_recolor_bug/README.md).  usage: flagged_warp_stress.py [reps]"""
 import os, sys, json, numpy as np, torch
-ROOT='/root/repo' if os.path.exists('/root/repo/tests') else os.getcwd()
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'tests'))
 import _libs, ecsimd_b200
 from ecsimd_b200 import host as eng, capi, device as dev

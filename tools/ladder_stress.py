@@ -1,5 +1,8 @@
+#!/usr/bin/env python3
+"""Every shipped ladder instance on device-resident random words, repeated: all runs must be bit-identical (no oracle:
+repeatability only).  usage: ladder_stress.py [runs] [log2 lanes] [layout:instance filter]"""
 import os, sys, json, numpy as np, torch
-ROOT='/root/repo' if os.path.exists('/root/repo/tests') else os.getcwd()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'tests'))
 import ecsimd_b200
 from ecsimd_b200 import device as dev, capi
