@@ -34,6 +34,7 @@ struct DeviceCtx {
   void* bounce_in[3] = {nullptr, nullptr, nullptr};   // pinned staging for pageable caller buffers
   void* bounce_out[3] = {nullptr, nullptr, nullptr};
   size_t bounce_in_bytes = 0, bounce_out_bytes = 0;
+  void* slot_dev[3] = {nullptr, nullptr, nullptr};    // device staging of one chunk per pipeline stream (k, P, result, affine result)
 };
 // context of the calling thread's current device, created on first use; nullptr + error set on failure
 DeviceCtx* current_ctx();

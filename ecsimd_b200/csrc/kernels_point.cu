@@ -94,22 +94,38 @@ __global__ void __launch_bounds__(PointThreads<OP>::value, PointThreads<OP>::blo
 // caller's layout directly (no conversion pass, no extra kernels competing for the SMs).
 // Scalar words and P are re-read from memory where they are needed (SrcGlobal) rather than held
 // in registers through the loop.
-template <int MODE, int L>
+// Scalar words 1..7 are staged once in shared memory (7 x THREADS words, each thread its own column), so that the
+// loop's only scalar input is one shared-memory address: the same loop for every layout (the pointer arithmetic of the
+// pack layout cost ptxas 50 instructions more per step than the other two).
+template <int MODE, int L, int THREADS>
 struct SrcGlobal {
   const void* k;
   const void* P;
   const uint4* tab;
   size_t n, i;
   int k_bcast;
-  __device__ __forceinline__ uint32_t kword(int w) const {
+  const uint32_t* sk;   // shared: word w of this lane's scalar at sk[(w - 1) * THREADS], w = 1..7
+  __device__ __forceinline__ uint32_t kword_global(int w) const {
     return k_bcast ? Layout<L_LANE>::load_word(k, 1, 0, 1, 0, w) : Layout<L>::load_word(k, n, i, 1, 0, w);
+  }
+  __device__ __forceinline__ uint32_t kword(int w) const {
+    if (w == 0) return kword_global(0);
+    return sk[(w - 1) * blockDim.x];
+  }
+  // the lane index, recomputed from the special registers and made opaque: nothing derived from it (the pack
+  // layout's (i >> 2, i & 3) pair, an SOA row address) is kept in registers through the loop for the code after it
+  static __device__ __forceinline__ size_t lane_index(size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    asm volatile("" : "+l"(t));
+    return t < n ? t : n - 1;
   }
   __device__ __forceinline__ void point(fe& x, fe& y) const {
     if (MODE == 0) {
       const void* p = P;
       asm volatile("" : "+l"(p));  // a fresh load each time: the value is not kept live through the loop
-      x = Layout<L>::load(p, n, i, 3, 0);
-      y = Layout<L>::load(p, n, i, 3, 1);
+      const size_t ii = lane_index(n);
+      x = Layout<L>::load(p, n, ii, 3, 0);
+      y = Layout<L>::load(p, n, ii, 3, 1);
     } else {
       const uint32_t gx[8] = ECB200_GXM_WORDS, gy[8] = ECB200_GYM_WORDS;
       x = fe_const(gx);
@@ -133,12 +149,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restric
                                                                  const uint4* __restrict__ tab) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = i0 < n ? i0 : n - 1;  // surplus threads recompute the last lane (they must reach the barriers)
-  const SrcGlobal<MODE, L> src{k, P, tab, n, i, k_bcast};
+  __shared__ uint32_t s_k[7 * THREADS];
+  const SrcGlobal<MODE, L, THREADS> src{k, P, tab, n, i, k_bcast, s_k + threadIdx.x};
+#pragma unroll
+  for (int w = 1; w < 8; w++) s_k[(w - 1) * THREADS + threadIdx.x] = src.kword_global(w);   // read back by the same thread only
   const jac r = pt_scalar_mult<QUIRK, true, TABW>(src);
-  if (i0 < n) {
-    Layout<L>::store(out, n, i, 3, 0, r.x);
-    Layout<L>::store(out, n, i, 3, 1, r.y);
-    Layout<L>::store(out, n, i, 3, 2, r.z);
+  size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // recomputed, not carried through the loop
+  asm volatile("" : "+l"(j0));
+  if (j0 < n) {
+    Layout<L>::store(out, n, j0, 3, 0, r.x);
+    Layout<L>::store(out, n, j0, 3, 1, r.y);
+    Layout<L>::store(out, n, j0, 3, 2, r.z);
   }
 }
 
@@ -384,6 +405,8 @@ int release_device_resources(DeviceCtx* c) {
   for (int i = 0; i < 3; i++) {
     if (c->pipe[i]) ECB_CUDA(cudaStreamDestroy(c->pipe[i]));
     c->pipe[i] = nullptr;
+    if (c->slot_dev[i]) ECB_CUDA(cudaFree(c->slot_dev[i]));
+    c->slot_dev[i] = nullptr;
     if (c->bounce_in[i]) ECB_CUDA(cudaFreeHost(c->bounce_in[i]));
     if (c->bounce_out[i]) ECB_CUDA(cudaFreeHost(c->bounce_out[i]));
     c->bounce_in[i] = c->bounce_out[i] = nullptr;
@@ -431,11 +454,19 @@ static int launch_ladder(int L, void* dout, const void* dk, const void* dP, int 
 //    pipeline.  The host copies of slot j happen while the other two slots run on the GPU.
 //  * affine = true appends to_affine to each chunk (ecb200_scalar_mult_p256_affine): the Jacobian result never
 //    crosses PCIe.
+//  * each stream owns the device buffers of its chunk (allocated once per device, 21 MiB per stream): chunk ci + 3
+//    reuses the buffers of chunk ci in the same stream, after that chunk's copy out.  Allocating them per chunk from
+//    the stream-ordered pool looked equivalent but is not: a block freed in one stream and handed to another makes
+//    the second stream wait for the first (the pool's internal dependency), i.e. the copy in of chunk ci + 1 waits
+//    for the copy out of chunk ci.
 constexpr size_t kChunkLanes = 148 * (size_t)kLadderThreads;
+constexpr size_t kSlotK = 0, kSlotP = kChunkLanes * 32, kSlotOut = kChunkLanes * 128, kSlotXY = kChunkLanes * 224, kSlotBytes = kChunkLanes * 288;
 static int pipe_resources(DeviceCtx* c, bool bounce) {
   std::lock_guard<std::mutex> lock(c->mu);
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < 3; i++) {
     if (!c->pipe[i]) ECB_CUDA(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+    if (!c->slot_dev[i]) ECB_CUDA(cudaMalloc(&c->slot_dev[i], kSlotBytes));
+  }
   if (bounce && !c->bounce_in[0]) {
     c->bounce_in_bytes = kChunkLanes * 128;
     c->bounce_out_bytes = kChunkLanes * 96;
@@ -491,14 +522,14 @@ static int host_pipeline_body(DeviceCtx* c, void* out, const void* k, const void
       done_lo[j] = lo;
       done_m[j] = m;
     }
-    Scratch sc(s);
+    Scratch sc(s);   // only the layouts without a native ladder instance need more than the slot's own buffers
     sc.ctx = c;
-    void *rk, *rP = nullptr, *ro, *rxy = nullptr;
-    if ((rc = sc.alloc(&rk, operand_bytes(m, 1))) || (rc = sc.alloc(&ro, operand_bytes(m, 3)))) return rc;
+    char* slot = (char*)c->slot_dev[j];
+    void *rk = slot + kSlotK, *rP = nullptr, *ro = slot + kSlotOut, *rxy = nullptr;
     // LANE and PACK4 are both contiguous per group of 4 lanes: a chunk is a byte range
     ECB_CUDA(cudaMemcpyAsync(rk, src_k, operand_bytes(m, 1), cudaMemcpyHostToDevice, s));
     if (mode == 0) {
-      if ((rc = sc.alloc(&rP, operand_bytes(m, 3)))) return rc;
+      rP = slot + kSlotP;
       ECB_CUDA(cudaMemcpyAsync(rP, src_P, operand_bytes(m, 3), cudaMemcpyHostToDevice, s));
     }
     if (native) {
@@ -516,7 +547,7 @@ static int host_pipeline_body(DeviceCtx* c, void* out, const void* k, const void
     }
     const void* res = ro;
     if (affine) {
-      if ((rc = sc.alloc(&rxy, operand_bytes(m, 2)))) return rc;
+      rxy = slot + kSlotXY;
       if ((rc = ecb200_to_affine(rxy, ro, m, dflags, s))) return rc;
       res = rxy;
     }

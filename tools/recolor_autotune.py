@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
-"""Several re-colourings of ONE shipped ladder kernel (different seeds of sass_recolor's search), each written as a
-complete kernels_point.cubin variant, to be timed on a GPU with tools/variant_bench.cu (KERNEL=<name>); `pick` then
-stores the fastest one's patch in csrc/recolor_plans.json.  The cost model of the search is fitted to +-0.2 %, so
-the variants differ by a few tenths of a percent on the device: this closes that gap by measurement.
+"""Several re-colourings of ONE shipped kernel (different seeds of sass_recolor's search; each one fully verified by the
+pass), written as code blobs that tools/recolor_bisect.py `run` patches into the original cubin and times on a GPU
+(with a repeat-stability count); `pick` then stores the fastest stable one's patch in csrc/recolor_plans.json.  The
+cost model of the search is fitted to +-0.2 %, and ptxas' own schedule differs between the instances of the ladder
+kernel, so instances differ by up to 1.7 % on the device: this closes that gap by measurement.
 
-  recolor_autotune.py gen  <kernel substring> <n seeds>      -> build/autotune/<tag>_s<seed>.cubin (+ list.txt)
-  recolor_autotune.py pick <kernel substring> <results.jsonl> -> updates recolor_plans.json (rebuild replays it)
+  recolor_autotune.py gen  <kernel substring> <tag> <n seeds>   -> build/bisect/<tag>_<seed>.bin, build/bisect/<tag>.json
+  (on the GPU box)  tools/recolor_bisect.py run <tag> 20 > gpurun_out/<tag>.jsonl
+  recolor_autotune.py pick <kernel substring> <tag> <results.jsonl>   -> updates recolor_plans.json (the build replays it)
 """
 import json
 import multiprocessing
@@ -18,50 +20,65 @@ sys.path.insert(0, CSRC)
 import sass_recolor as rc  # noqa: E402
 
 CUBIN = os.path.join(ROOT, "build", "obj", "kernels_point.cu.keep", "kernels_point.cubin.orig")
-OUT = os.path.join(ROOT, "build", "autotune")
+OUT = os.path.join(ROOT, "build", "bisect")
 PLANS = os.path.join(CSRC, "recolor_plans.json")
 
 
 def _one(args):
     sec, seed, tag = args
     r = rc.recolour_section(CUBIN, sec, iters=30000, seed=seed)
-    blob = bytearray(open(CUBIN, "rb").read())
-    blob[r["offset"]:r["offset"] + len(r["code"])] = r["code"]
-    path = os.path.join(OUT, "%s_s%d.cubin" % (tag, seed))
-    open(path, "wb").write(bytes(blob))
-    return path, r["cost_after"]
+    path = os.path.join(OUT, "%s_%05d.bin" % (tag, seed))
+    open(path, "wb").write(r["code"])
+    return os.path.relpath(path, ROOT), r["cost_after"], r["offset"], len(r["code"])
 
 
 def main():
-    mode, sub = sys.argv[1], sys.argv[2]
+    mode, sub, tag = sys.argv[1], sys.argv[2], sys.argv[3]
     blob = open(CUBIN, "rb").read()
     secs = [n for n in rc.elf_sections(blob) if n.startswith(".text.") and sub in n]
     assert len(secs) == 1, secs
     sec = secs[0]
-    tag = "".join(ch for ch in sub if ch.isalnum())[-24:]
     os.makedirs(OUT, exist_ok=True)
+    off, size, _ = rc.elf_sections(blob)[sec]
     if mode == "gen":
-        n = int(sys.argv[3])
+        n = int(sys.argv[4])
         with multiprocessing.Pool(min(n, os.cpu_count() or 1)) as pool:
             res = pool.map(_one, [(sec, 100 + s, tag) for s in range(n)], chunksize=1)
-        for p, c in res:
+        files = []
+        # variant 0 = what ptxas wrote, variant 1 = the patch the build replays now
+        open(os.path.join(OUT, "%s_00000.bin" % tag), "wb").write(blob[off:off + size])
+        files.append(os.path.relpath(os.path.join(OUT, "%s_00000.bin" % tag), ROOT))
+        plans = json.load(open(PLANS))
+        if sec in plans and plans[sec]["key"] == rc.code_hash(blob[off:off + size]):
+            cur = bytes(a ^ b for a, b in zip(blob[off:off + size], rc._unpack(plans[sec]["xor"])))
+            open(os.path.join(OUT, "%s_00001.bin" % tag), "wb").write(cur)
+            files.append(os.path.relpath(os.path.join(OUT, "%s_00001.bin" % tag), ROOT))
+        for p, c, o, sz in res:
             print(p, round(c, 2))
-        open(os.path.join(OUT, "%s_list.txt" % tag), "w").write(" ".join(os.path.relpath(p, ROOT) for p, _ in res))
-        print("KERNEL=%s" % sec[len(".text."):])
+            files.append(p)
+        json.dump({"sec": sec, "off": off, "size": size, "files": files, "costs": {p: c for p, c, o, sz in res}}, open(os.path.join(OUT, "%s.json" % tag), "w"))
     else:
         best = None
-        for l in open(sys.argv[3]):
+        for l in open(sys.argv[4]):
             if '"variant"' in l:
                 d = json.loads(l)
-                if tag in d["variant"] and (best is None or d["ms"] < best["ms"]):
+                name = os.path.basename(d["variant"])
+                if not name.startswith(tag + "_") or d.get("unstable_runs", 0) or name.endswith("_00000.cubin"):
+                    continue
+                if best is None or d["ms"] < best["ms"]:
                     best = d
         print("best:", best)
-        off, size, _ = rc.elf_sections(blob)[sec]
         code = blob[off:off + size]
-        new = open(os.path.join(ROOT, best["variant"]), "rb").read()[off:off + size]
+        new = open(os.path.join(OUT, os.path.basename(best["variant"]).replace(".cubin", ".bin")), "rb").read()
+        assert len(new) == size
         plans = json.load(open(PLANS))
+        meta = json.load(open(os.path.join(OUT, "%s.json" % tag)))
         plans[sec].update({"key": rc.code_hash(code), "patched_key": rc.code_hash(new), "xor": rc._pack(bytes(a ^ b for a, b in zip(code, new))),
                            "autotuned_ms_2p20": best["ms"]})
+        plans[sec].pop("census_after", None)          # belonged to the patch this one replaces
+        rel = os.path.relpath(os.path.join(OUT, os.path.basename(best["variant"]).replace(".cubin", ".bin")), ROOT)
+        if rel in meta.get("costs", {}):
+            plans[sec]["cost_after"] = meta["costs"][rel]
         json.dump(plans, open(PLANS, "w"), indent=0, sort_keys=True)
 
 
