@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(PointThreads<OP>::value, PointThreads<OP>::blo
 // caller's layout directly (no conversion pass, no extra kernels competing for the SMs).
 // Scalar words and P are re-read from memory where they are needed (SrcGlobal) rather than held
 // in registers through the loop.
-// Scalar words 1..7 are staged once in shared memory (7 x THREADS words, each thread its own column), so that the
+#ifndef SK_STRIDE
+#define SK_STRIDE blockDim.x
+#endif
+// The scalar is staged once in shared memory (8 x THREADS words, each thread its own column), so that the
 // loop's only scalar input is one shared-memory address: the same loop for every layout (the pointer arithmetic of the
 // pack layout cost ptxas 50 instructions more per step than the other two).
 template <int MODE, int L, int THREADS>
@@ -104,14 +107,11 @@ struct SrcGlobal {
   const uint4* tab;
   size_t n, i;
   int k_bcast;
-  const uint32_t* sk;   // shared: word w of this lane's scalar at sk[(w - 1) * THREADS], w = 1..7
+  const uint32_t* sk;   // shared: word w of this lane's scalar at sk[w * THREADS], w = 0..7
   __device__ __forceinline__ uint32_t kword_global(int w) const {
     return k_bcast ? Layout<L_LANE>::load_word(k, 1, 0, 1, 0, w) : Layout<L>::load_word(k, n, i, 1, 0, w);
   }
-  __device__ __forceinline__ uint32_t kword(int w) const {
-    if (w == 0) return kword_global(0);
-    return sk[(w - 1) * blockDim.x];
-  }
+  __device__ __forceinline__ uint32_t kword(int w) const { return sk[w * SK_STRIDE]; }
   // the lane index, recomputed from the special registers and made opaque: nothing derived from it (the pack
   // layout's (i >> 2, i & 3) pair, an SOA row address) is kept in registers through the loop for the code after it
   static __device__ __forceinline__ size_t lane_index(size_t n) {
@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_scalar_mult_sync(void* __restric
                                                                  const uint4* __restrict__ tab) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = i0 < n ? i0 : n - 1;  // surplus threads recompute the last lane (they must reach the barriers)
-  __shared__ uint32_t s_k[7 * THREADS];
+  __shared__ uint32_t s_k[8 * THREADS];
   const SrcGlobal<MODE, L, THREADS> src{k, P, tab, n, i, k_bcast, s_k + threadIdx.x};
 #pragma unroll
-  for (int w = 1; w < 8; w++) s_k[(w - 1) * THREADS + threadIdx.x] = src.kword_global(w);   // read back by the same thread only
+  for (int w = 0; w < 8; w++) s_k[w * THREADS + threadIdx.x] = src.kword_global(w);   // read back by the same thread only
   const jac r = pt_scalar_mult<QUIRK, true, TABW>(src);
   size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // recomputed, not carried through the loop
   asm volatile("" : "+l"(j0));

@@ -134,12 +134,12 @@ TU = r'''
 #include "../../ecsimd_b200/csrc/layout.cuh"
 #include "../../ecsimd_b200/csrc/point.cuh"
 using namespace ecb200;
-// the same inputs as k_scalar_mult_sync (kernels_point.cu): scalar words 1..7 staged in shared memory, the lane index
+// the same inputs as k_scalar_mult_sync (kernels_point.cu): the scalar staged in shared memory, the lane index
 // recomputed after the loop -- the loop's live set decides how many moves and spills ptxas adds
 struct SrcG {
   const void* k; const void* P; size_t n, i; const uint32_t* sk;
   __device__ __forceinline__ uint32_t kword_global(int w) const { return Layout<L_SOA>::load_word(k, n, i, 1, 0, w); }
-  __device__ __forceinline__ uint32_t kword(int w) const { return w == 0 ? kword_global(0) : sk[(w - 1) * blockDim.x]; }
+  __device__ __forceinline__ uint32_t kword(int w) const { return sk[w * blockDim.x]; }
   __device__ __forceinline__ void point(fe& x, fe& y) const {
     const void* p = P; asm volatile("" : "+l"(p));
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; asm volatile("" : "+l"(t));
@@ -151,10 +151,10 @@ struct SrcG {
 extern "C" __global__ void __launch_bounds__(512, 1) k_ladder(void* __restrict__ out, const void* __restrict__ k, const void* __restrict__ P, size_t n) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = i0 < n ? i0 : n - 1;
-  __shared__ uint32_t s_k[7 * 512];
+  __shared__ uint32_t s_k[8 * 512];
   const SrcG src{k, P, n, i, s_k + threadIdx.x};
 #pragma unroll
-  for (int w = 1; w < 8; w++) s_k[(w - 1) * 512 + threadIdx.x] = src.kword_global(w);
+  for (int w = 0; w < 8; w++) s_k[w * 512 + threadIdx.x] = src.kword_global(w);
   const jac r = pt_scalar_mult<true, true, 0>(src);
   size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; asm volatile("" : "+l"(j0));
   if (j0 < n) { Layout<L_SOA>::store(out, n, j0, 3, 0, r.x); Layout<L_SOA>::store(out, n, j0, 3, 1, r.y); Layout<L_SOA>::store(out, n, j0, 3, 2, r.z); }
