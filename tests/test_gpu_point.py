@@ -328,3 +328,43 @@ def test_flagged_lanes_under_load_are_repeatable(eng, orc):
             again = eng.scalar_mult(kl, Pl, layout=layout)
             bad = np.nonzero((back(again, 3) != back(first, 3)).any(axis=1))[0]
             assert len(bad) == 0, "%s run %d: lanes %s differ from the first run" % (layout, rep + 2, bad[:8].tolist())
+
+
+def test_point_and_affine_kernels_are_repeatable_at_full_occupancy(eng, orc):
+    """The other re-coloured kernels (five point operations, to_affine, inverse, from_x) on 2^19 lanes -- several waves
+    of two 256-thread blocks per SM -- with a share of lanes that take their out-of-line exact paths (all-ones words:
+    every 2^-32 case of the conditional subtractions): three runs identical, sampled lanes equal to the oracle."""
+    n = 1 << 19
+    base = _points(orc, 256, 0xEC51D031)
+    A = base[np.arange(n) % 256].copy()
+    B = base[(np.arange(n) * 7 + 3) % 256].copy()
+    A[5::64, :16] = 0xFFFFFFFF                      # out of contract: drives the flagged-lane paths under load
+    B[9::128, 8:16] = 0xFFFFFFFF
+    idx = np.unique(np.concatenate([np.arange(128), np.arange(n - 64, n), np.arange(5, n, 6400), np.arange(9, n, 12800)]))
+
+    def check(name, run, want):
+        first = run()
+        first = first if isinstance(first, tuple) else (first,)
+        for rep in range(2):
+            again = run()
+            again = again if isinstance(again, tuple) else (again,)
+            for a, f in zip(again, first):
+                assert np.array_equal(a, f), "%s: run %d differs from the first" % (name, rep + 2)
+        want = want if isinstance(want, tuple) else (want,)
+        for f, w in zip(first, want):
+            assert np.array_equal(f[idx], w), "%s vs oracle" % name
+
+    check("DBLU", lambda: eng.DBLU(A), orc.dblu(A[idx]))
+    check("TRPLU", lambda: eng.TRPLU(A), orc.trplu(A[idx]))
+    check("ZADDU", lambda: eng.ZADDU(A, B), orc.zaddu(A[idx], B[idx]))
+    check("ZDAU", lambda: eng.ZDAU(A, B), orc.zdau(A[idx], B[idx]))
+    check("ADD_Z2_1", lambda: eng.ADD_Z2_1(A, B), orc.add_z2_1(A[idx], B[idx]))
+    check("to_affine", lambda: eng.to_affine(A), orc.to_affine(A[idx]))
+    x = A[:, :8].copy()
+    check("inverse", lambda: eng.inverse(x), orc.inverse(x[idx]))
+    first = eng.from_x(x)
+    for rep in range(2):
+        again = eng.from_x(x)
+        assert np.array_equal(again[0], first[0]) and np.array_equal(again[1], first[1]), "from_x: run %d differs" % (rep + 2)
+    sub = eng.from_x(np.ascontiguousarray(x[idx]))
+    assert np.array_equal(sub[0], first[0][idx]) and np.array_equal(sub[1], first[1][idx])      # batch size does not matter
