@@ -553,10 +553,13 @@ static int host_pipeline_body(DeviceCtx* c, void* out, const void* k, const void
     }
     ECB_CUDA(cudaMemcpyAsync(dst, res, m * out_lane, cudaMemcpyDeviceToHost, s));
   }
-  for (int j = 0; j < 3; j++) {
+  // the last (up to) three chunks, oldest first: the host copy out of one overlaps the GPU work of the next
+  for (size_t t = ci >= 3 ? ci - 3 : 0; t < ci; t++) {
+    const int j = (int)(t % 3);
     ECB_CUDA(cudaStreamSynchronize(ss[j]));
     if (bounce && done_m[j]) memcpy((char*)out + done_lo[j] * out_lane, c->bounce_out[j], done_m[j] * out_lane);
   }
+  for (int j = 0; j < 3; j++) ECB_CUDA(cudaStreamSynchronize(ss[j]));   // fewer than three chunks: idle streams, no-op
   return ECB200_OK;
 }
 
